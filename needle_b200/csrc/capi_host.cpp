@@ -1,0 +1,124 @@
+// C ABI, host half: regex -> blob, blob introspection, error plumbing.  See include/needle_b200.h.
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "capi_internal.h"
+#include "host/ast.h"
+#include "host/pattern.h"
+#include "needle_b200.h"
+
+namespace ndl {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+// UTF-8 -> UTF-16 code units (BMP and surrogate pairs for the rest, like a Java string literal).
+static bool utf8_to_utf16(const char* s, std::u16string& out) {
+  const unsigned char* p = reinterpret_cast<const unsigned char*>(s);
+  while (*p) {
+    uint32_t cp;
+    int extra;
+    if (*p < 0x80) { cp = *p; extra = 0; }
+    else if ((*p & 0xE0) == 0xC0) { cp = *p & 0x1F; extra = 1; }
+    else if ((*p & 0xF0) == 0xE0) { cp = *p & 0x0F; extra = 2; }
+    else if ((*p & 0xF8) == 0xF0) { cp = *p & 0x07; extra = 3; }
+    else return false;
+    p++;
+    for (int i = 0; i < extra; i++, p++) {
+      if ((*p & 0xC0) != 0x80) return false;
+      cp = (cp << 6) | (*p & 0x3F);
+    }
+    if (cp >= 0x10000) {
+      cp -= 0x10000;
+      out.push_back(static_cast<char16_t>(0xD800 + (cp >> 10)));
+      out.push_back(static_cast<char16_t>(0xDC00 + (cp & 0x3FF)));
+    } else {
+      out.push_back(static_cast<char16_t>(cp));
+    }
+  }
+  return true;
+}
+
+static int compile_to_blob(const std::u16string& regex, int flags, uint8_t** blob_out, size_t* blob_len_out) {
+  if (!blob_out || !blob_len_out) return fail(NDL_EINVAL, "blob_out / blob_len_out must not be NULL");
+  *blob_out = nullptr;
+  *blob_len_out = 0;
+  try {
+    CompiledPattern p = compile_pattern(regex, flags);
+    std::vector<uint8_t> bytes = serialize_pattern(p);
+    uint8_t* mem = static_cast<uint8_t*>(std::malloc(bytes.size()));
+    if (!mem) return fail(NDL_ENOMEM, "out of memory");
+    std::memcpy(mem, bytes.data(), bytes.size());
+    *blob_out = mem;
+    *blob_len_out = bytes.size();
+    return NDL_OK;
+  } catch (const SyntaxError& e) {
+    return fail(NDL_ESYNTAX, e.what());
+  } catch (const TooLargeError& e) {
+    return fail(NDL_ETOOLARGE, e.what());
+  } catch (const FlagsError& e) {
+    return fail(NDL_EFLAGS, e.what());
+  } catch (const CompileError& e) {
+    return fail(NDL_ECOMPILE, e.what());
+  } catch (const std::bad_alloc&) {
+    return fail(NDL_ENOMEM, "out of memory");
+  } catch (const std::exception& e) {
+    return fail(NDL_ECOMPILE, e.what());
+  }
+}
+
+}  // namespace ndl
+
+using namespace ndl;
+
+extern "C" {
+
+int ndl_compile(const uint16_t* regex_utf16, size_t n_chars, int flags, uint8_t** blob_out, size_t* blob_len_out) {
+  if (!regex_utf16 && n_chars) return fail(NDL_EINVAL, "regex string cannot be null");
+  std::u16string regex(reinterpret_cast<const char16_t*>(regex_utf16), n_chars);
+  return compile_to_blob(regex, flags, blob_out, blob_len_out);
+}
+
+int ndl_compile_utf8(const char* regex_utf8, int flags, uint8_t** blob_out, size_t* blob_len_out) {
+  if (!regex_utf8) return fail(NDL_EINVAL, "regex string cannot be null");
+  std::u16string regex;
+  if (!utf8_to_utf16(regex_utf8, regex)) return fail(NDL_EINVAL, "regex is not valid UTF-8");
+  return compile_to_blob(regex, flags, blob_out, blob_len_out);
+}
+
+void ndl_blob_free(uint8_t* blob) { std::free(blob); }
+
+int ndl_blob_info_get(const uint8_t* blob, size_t blob_len, ndl_blob_info* out) {
+  if (!out) return fail(NDL_EINVAL, "out must not be NULL");
+  try {
+    CompiledPattern p = deserialize_pattern(blob, blob_len);
+    out->version = kBlobVersion;
+    out->flags = p.flags;
+    out->min_length = p.min_length;
+    out->max_length = p.max_length;
+    out->stride = p.stride;
+    out->byte_class_count = p.byte_class_count;
+    out->reverse_mode = p.reverse_mode;
+    out->reverse_char = p.reverse_char;
+    for (int k = 0; k < 4; k++) {
+      out->n_states[k] = p.tables[k].n_states;
+      out->entry_width[k] = p.tables[k].width;
+      out->max_char[k] = p.tables[k].max_char;
+      out->n_accepting[k] = p.tables[k].n_accepting();
+    }
+    return NDL_OK;
+  } catch (const std::exception& e) {
+    return fail(NDL_EBLOB, e.what());
+  }
+}
+
+const char* ndl_last_error(void) { return g_last_error.c_str(); }
+
+const char* ndl_version(void) { return "needle_b200 0.1.0 (blob v1, sm_100a)"; }
+
+}  // extern "C"
