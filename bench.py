@@ -1,0 +1,326 @@
+#!/usr/bin/env python3
+"""bench.py - the reference's headline metric on B200: input GB/s scanned (+ matches/s) by the DFA match
+hot path, next to the CPU restatement of the reference's generated loops on the box's host cores.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c4b|c3]
+
+A "step" is one pass of find() over one batch of synthetic haystacks.  Default workload = BASELINE.json
+configs[1]: `\\d{3}-\\d{2}-\\d{4}` over 10 M synthetic 64-byte ASCII lines per GPU (640 MB, larger than
+the 126 MB L2, so every step streams from HBM).  N > 1 is launched by torchrun, one rank per GPU; the
+regex is compiled on rank 0 and its table blob is NCCL-broadcast; haystack batches are sharded by rank
+(weak scaling: each GPU scans its own 10 M lines) with no data-path collective.
+
+`value`  whole-job GB/s with inputs resident in HBM (device pointers through ndl_match_batch).
+`e2e`    same metric through ndl_match_batch with HOST (pinned) buffers: H2D of data+offsets and D2H of
+         the results inside the timed region.
+`--impl reference`  the reference arm: needle's own code is JVM bytecode generated at run time and no JVM
+         exists on this image, so it times the C restatement of the generated loops (oracle/, kind "port")
+         on all host cores, on the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from tests import workloads  # noqa: E402
+
+METRIC = "input_gb_per_s_scanned"
+UNIT = "GB/s"
+
+WORKLOADS = {
+    # name: (regex key, description, generator, default lines per GPU, char width)
+    "c2": ("c2", "BASELINE configs[1]: '\\d{3}-\\d{2}-\\d{4}' find() over 10M synthetic 64-byte ASCII lines per GPU", workloads.c2_lines, 10_000_000, 1),
+    "c4b": ("c4", "BASELINE configs[3] batched variant: 256-state DFA 'a[ab]{7}c' find() over 64-byte lines of {a,b}", workloads.c4_lines, 10_000_000, 1),
+    "c3": ("c3", "BASELINE configs[2]: email-like regex find() over mixed-length lines (8..120 B)", workloads.c3_lines, 10_000_000, 1),
+}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, rank, world):
+    """The reference arm: the C restatement of the reference's generated loops on the host cores."""
+    if rank != 0:
+        return
+    import needle_b200 as nb
+    from tests.oracle_lib import Oracle
+
+    key, desc, gen, default_lines, cw = WORKLOADS[args.workload]
+    regex = workloads.REGEX[key]
+    ora = Oracle(nb.compile_to_bytes(regex, 0))
+    threads = host_threads()
+    n_sample = min(args.lines or default_lines, 2_000_000)
+    data, offsets = gen(n_sample)
+    in_bytes = int(offsets[-1] - offsets[0]) * cw
+    for _ in range(args.warmup):
+        ora.match_batch(2, data, offsets, cw, threads=threads)
+    t0 = time.perf_counter()
+    matches = 0
+    for _ in range(args.steps):
+        m, _, _ = ora.match_batch(2, data, offsets, cw, threads=threads)
+        matches = int(m.sum())
+    dt = time.perf_counter() - t0
+    gbs = in_bytes * args.steps / dt / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gbs, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": desc, "regex": regex, "mode": "find", "lines_per_step": n_sample, "bytes_per_step": in_bytes,
+                   "note": "no JVM on this image: C restatement of needle's generated Matcher loops (oracle/), all host threads"},
+        "matches_per_s": matches * args.steps / dt,
+        "cpu_baseline": {"value": gbs, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{n_sample} lines ({in_bytes / 1e6:.0f} MB) of the workload per step"},
+        "e2e": {"value": gbs, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+
+    import needle_b200 as nb
+    from needle_b200 import _lib
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    key, desc, gen, default_lines, cw = WORKLOADS[args.workload]
+    regex = workloads.REGEX[key]
+    n = args.lines or default_lines
+
+    # regex -> table blob on rank 0; ONE NCCL broadcast of the blob; every rank uploads its own device image
+    if rank == 0:
+        blob = nb.compile_to_bytes(regex, 0)
+        size = torch.tensor([len(blob)], dtype=torch.int64, device=dev)
+    else:
+        blob, size = None, torch.zeros(1, dtype=torch.int64, device=dev)
+    if dist:
+        dist.broadcast(size, 0)
+        buf = torch.empty(int(size.item()), dtype=torch.uint8, device=dev)
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(blob), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        blob = bytes(buf.cpu().numpy().tobytes())
+    pat = nb.Pattern(blob, device=local_rank)
+
+    # this rank's shard of the job: its own n lines (weak scaling), seeded by rank
+    data_h, off_h = gen(n, seed=0x5EED0000 + 16 * rank + int(key[1]))
+    in_bytes = int(off_h[-1] - off_h[0]) * cw
+    pin = torch.cuda.is_available()
+    data_p = torch.from_numpy(data_h).pin_memory() if pin else torch.from_numpy(data_h)
+    off_p = torch.from_numpy(off_h.view(np.int64)).pin_memory()
+    data_d, off_d = data_p.to(dev), off_p.to(dev)
+    matched_d = torch.zeros(n, dtype=torch.uint8, device=dev)
+    start_d = torch.zeros(n, dtype=torch.int32, device=dev)
+    end_d = torch.zeros(n, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        pat.match_batch_ptrs(nb.MODE_FIND, data_d.data_ptr(), off_d.data_ptr(), n, cw, matched_d.data_ptr(), start_d.data_ptr(),
+                             end_d.data_ptr(), stream=stream.cuda_stream)
+
+    def sync_all():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+
+    # parity guard (untimed): a sample of the batch against the oracle; a mismatch voids the run
+    from tests.oracle_lib import Oracle
+    ns = min(n, 200_000)
+    em, es, ee = Oracle(blob).match_batch(2, data_h, off_h[:ns + 1], cw, threads=host_threads())
+    if not (np.array_equal(matched_d[:ns].cpu().numpy(), em) and np.array_equal(start_d[:ns].cpu().numpy(), es)
+            and np.array_equal(end_d[:ns].cpu().numpy(), ee)):
+        raise SystemExit("bench: GPU results differ from the oracle - refusing to report a number")
+
+    # ---- timed region 1: inputs resident in HBM
+    sampler = ClockSampler(local_rank)
+    launches0 = _lib.lib().ndl_kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    sampler.start()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    ev1.record(stream)
+    sync_all()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = _lib.lib().ndl_kernel_launches() - launches0
+    n_matches = int(matched_d.sum().item())
+
+    # ---- timed region 2: end to end from pinned host buffers through the same C-ABI call
+    matched_h = torch.zeros(n, dtype=torch.uint8).pin_memory()
+    start_h = torch.zeros(n, dtype=torch.int32).pin_memory()
+    end_h = torch.zeros(n, dtype=torch.int32).pin_memory()
+    e2e_steps = max(1, min(args.steps, 5))
+
+    def step_host():
+        pat.match_batch_ptrs(nb.MODE_FIND, data_p.data_ptr(), off_p.data_ptr(), n, cw, matched_h.data_ptr(), start_h.data_ptr(),
+                             end_h.data_ptr(), mem_kind=nb.MEM_HOST, stream=stream.cuda_stream)
+
+    step_host()
+    sync_all()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        step_host()
+    e1.record(stream)
+    sync_all()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    assert np.array_equal(matched_h[:ns].numpy(), em)
+
+    # max over ranks, sum of bytes over ranks
+    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(in_bytes), float(n_matches), float(launches)], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms, e2e_ms = t.tolist()
+    job_bytes, job_matches, job_launches = tot.tolist()
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        value = job_bytes * args.steps / (ms * 1e-3) / 1e9
+        e2e_value = job_bytes * e2e_steps / (e2e_ms * 1e-3) / 1e9
+        kernel_ms = ms / args.steps  # one kernel launch per step
+        achieved = in_bytes / (kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": desc, "regex": regex, "mode": "find", "lines_per_gpu": n, "bytes_per_gpu_per_step": in_bytes,
+                       "l2": "inputs (640 MB per step) are larger than the 126 MB L2; no flush needed",
+                       "sharding": "contiguous line ranges per rank, table blob NCCL-broadcast once, no data-path collective"},
+            "matches_per_s": job_matches * args.steps / (ms * 1e-3),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(in_bytes + off_h.nbytes), "d2h_bytes_per_step": int(9 * n),
+                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+            "gpu_launches": int(job_launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "lines8_kernel", "kernel_ms": kernel_ms, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": in_bytes,
+                         "note": "algorithmic bytes = haystack bytes only (SURVEY.md 8d); the launch also reads 8 B/line of offsets and writes 9 B/line of results"},
+        }
+        if world == 1:
+            line["cpu_baseline"] = cpu_baseline(blob, data_h, off_h, cw)
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(blob, data, offsets, cw):
+    """The oracle port timed on this box's host cores on a bounded sample of the same workload."""
+    from tests.oracle_lib import Oracle
+    ora = Oracle(blob)
+    threads = host_threads()
+    n = min(len(offsets) - 1, 1_000_000)
+    t0 = time.perf_counter()
+    ora.match_batch(2, data, offsets[:n + 1], cw, threads=threads)
+    calib = time.perf_counter() - t0
+    reps = int(max(1, min(200, 10.0 / max(calib, 1e-3))))  # ~10 s of CPU work
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ora.match_batch(2, data, offsets[:n + 1], cw, threads=threads)
+    dt = time.perf_counter() - t0
+    nbytes = int(offsets[n] - offsets[0]) * cw
+    return {"value": nbytes * reps / dt / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"first {n} lines ({nbytes / 1e6:.0f} MB) x {reps} passes, {threads} threads; C restatement of the generated loops, not the JVM"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--lines", type=int, default=0, help="lines per GPU (default: the workload's full size)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

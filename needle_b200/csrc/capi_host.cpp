@@ -122,3 +122,38 @@ const char* ndl_last_error(void) { return g_last_error.c_str(); }
 const char* ndl_version(void) { return "needle_b200 0.1.0 (blob v1, sm_100a)"; }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Test hook (not part of include/needle_b200.h): exposes intermediate results of the host pipeline so
+// that the reference's structure tests (NFAToDFACompilerTest.java:11-35, DFATest.java:186-352) can be
+// replayed.  conversion_mode: 0 BASIC, 1 CONTAINED_IN, 2 DFA_SEARCH.  The NFA is built with
+// leftMostLongest = true, like RegexInstrBuilder.createNFA(ast) which those tests go through.
+// ---------------------------------------------------------------------------------------------
+#include "host/automata.h"
+
+extern "C" int ndl_debug_dfa(const uint16_t* regex_utf16, size_t n_chars, int flags, int conversion_mode,
+                             int32_t* raw_states, int32_t* minimized_states, uint8_t* byte_classes_65536) {
+  try {
+    std::u16string regex(reinterpret_cast<const char16_t*>(regex_utf16), n_chars);
+    Ast ast;
+    Node* node = parse_regex(ast, regex, flags);
+    std::vector<Instr> prog = build_program(node, true);
+    ConversionMode mode = conversion_mode == 0 ? ConversionMode::Basic
+                          : conversion_mode == 1 ? ConversionMode::ContainedIn : ConversionMode::DfaSearch;
+    std::unique_ptr<Dfa> raw = subset_construction(prog, mode);
+    if (raw_states) *raw_states = raw->count();
+    raw->prune_dead_states();
+    std::unique_ptr<Dfa> m = minimize(*raw);
+    if (minimized_states) *minimized_states = m->count();
+    if (byte_classes_65536) {
+      ByteClasses bc = byte_classes(*m);
+      if (!bc.present) return fail(NDL_ECOMPILE, "no byte classes");
+      for (int c = 0; c < 65536; c++) byte_classes_65536[c] = bc.ranges[c];
+    }
+    return NDL_OK;
+  } catch (const SyntaxError& e) {
+    return fail(NDL_ESYNTAX, e.what());
+  } catch (const std::exception& e) {
+    return fail(NDL_ECOMPILE, e.what());
+  }
+}

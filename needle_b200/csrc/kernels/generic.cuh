@@ -1,0 +1,122 @@
+// Generic batch kernel: one haystack per thread, any char width, any table size, tables read from
+// global memory through the read-only path.  This is the shape-agnostic path (UTF-16 input, DFAs too
+// large for shared memory, arbitrarily long haystacks); the tuned byte-input kernels live in
+// lines8.cuh.  Same device automaton (device_image.h), same results.
+#pragma once
+#include <cstdint>
+
+namespace ndl {
+
+struct DevTable {
+  const uint16_t* cmap;   // 65536 entries: char -> class column
+  const uint16_t* trans;  // (n_states + 1) * n_classes
+  const uint8_t* accept;  // n_states + 1
+  int n_states;           // DEAD == n_states
+  int n_classes;
+  int root_accepting;
+};
+
+struct BatchParams {
+  const void* data;
+  const uint64_t* offsets;  // n + 1, in chars
+  const int32_t* from;      // nullable
+  uint8_t* matched;
+  int32_t* start;           // nullable unless mode == find
+  int32_t* end;
+  uint64_t n;
+  int mode;
+  int min_length, max_length;
+  int reverse_mode, reverse_char;
+  DevTable fwd;  // the table the mode walks forwards: MATCHES / CONTAINEDIN / FORWARDS
+  DevTable bwd;  // BACKWARDS (find only)
+};
+
+template <typename CharT>
+__device__ __forceinline__ int dev_step(const DevTable& t, int state, CharT c) {
+  return __ldg(t.trans + state * t.n_classes + __ldg(t.cmap + c));
+}
+
+// matches(): DFAClassBuilder.java:854-912.
+template <typename CharT>
+__device__ __forceinline__ bool dev_matches(const BatchParams& p, const CharT* s, int64_t len) {
+  if (p.min_length > 4 && p.min_length > len) return false;  // DFAMethodComponents.java:75-93
+  if (p.max_length != -1 && len > p.max_length) return false;
+  const int dead = p.fwd.n_states;
+  int state = 0;
+  for (int64_t i = 0; i < len; i++) {
+    state = dev_step(p.fwd, state, s[i]);
+    if (state == dead) return false;
+  }
+  return __ldg(p.fwd.accept + state) != 0;
+}
+
+// containedIn(): DFAClassBuilder.java:956-1025 (accepting rows are absorbing in the device table).
+template <typename CharT>
+__device__ __forceinline__ bool dev_contained_in(const BatchParams& p, const CharT* s, int64_t len) {
+  int state = 0;
+  for (int64_t i = 0; i < len; i++) {
+    if (__ldg(p.fwd.accept + state)) return true;
+    state = dev_step(p.fwd, state, s[i]);
+  }
+  return __ldg(p.fwd.accept + state) != 0;
+}
+
+// indexForwards(from, _): DFAClassBuilder.java:335-471.
+template <typename CharT>
+__device__ __forceinline__ int64_t dev_index_forwards(const BatchParams& p, const CharT* s, int64_t len, int64_t from) {
+  const int dead = p.fwd.n_states;
+  int state = 0;
+  // root accepting: `lastMatch = 0`, then the top-of-loop wasAccepted check of the first iteration sets it to `from`
+  int64_t last = p.fwd.root_accepting ? (from < len ? from : 0) : -1;
+  for (int64_t i = from; i < len; i++) {
+    state = dev_step(p.fwd, state, s[i]);
+    if (state == dead) return last;
+    if (__ldg(p.fwd.accept + state)) last = i + 1;
+  }
+  return last;
+}
+
+// indexBackwards(index = end - 1, lowerBound = from): DFAClassBuilder.java:529-614.
+template <typename CharT>
+__device__ __forceinline__ int64_t dev_index_backwards(const BatchParams& p, const CharT* s, int64_t index, int64_t lower,
+                                                       int64_t int_max) {
+  if (p.reverse_mode == 1) {  // single-char reverse scan
+    for (; index >= lower; index--)
+      if (static_cast<int>(s[index]) == p.reverse_char) return index;
+    return int_max;
+  }
+  const int dead = p.bwd.n_states;
+  int64_t last = p.bwd.root_accepting ? lower : int_max;
+  int state = 0;
+  for (; index >= lower; index--) {
+    state = dev_step(p.bwd, state, s[index]);
+    if (state == dead) return last;
+    if (__ldg(p.bwd.accept + state)) last = index;
+  }
+  return last;
+}
+
+template <typename CharT>
+__global__ void __launch_bounds__(256) generic_batch_kernel(const BatchParams p) {
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+    const uint64_t o0 = p.offsets[i], o1 = p.offsets[i + 1];
+    const CharT* s = static_cast<const CharT*>(p.data) + o0;
+    const int64_t len = static_cast<int64_t>(o1 - o0);
+    if (p.mode == 0) {
+      p.matched[i] = dev_matches(p, s, len);
+    } else if (p.mode == 1) {
+      p.matched[i] = dev_contained_in(p, s, len);
+    } else {
+      const int64_t from = p.from ? p.from[i] : 0;
+      const int64_t e = dev_index_forwards(p, s, len, from);  // find(from, to): DFAClassBuilder.java:625-659
+      int64_t st = -1;
+      if (e != -1) st = (p.reverse_mode == 2) ? e - p.min_length : dev_index_backwards(p, s, e - 1, from, 0x7fffffff);
+      p.matched[i] = e != -1;
+      p.start[i] = static_cast<int32_t>(st);
+      p.end[i] = static_cast<int32_t>(e);
+    }
+  }
+}
+
+}  // namespace ndl

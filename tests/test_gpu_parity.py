@@ -1,0 +1,267 @@
+"""GPU parity: the CUDA kernels, called through the C ABI (ndl_match_batch), against the CPU oracle and
+the reference's golden vectors - bit exact on (matched, start, end).  Needs a CUDA device."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import needle_b200 as nb
+from needle_b200 import _lib
+from tests import kats, workloads
+from tests.oracle_lib import Oracle
+
+pytestmark = pytest.mark.gpu
+
+_P = {}
+
+
+def pair(regex, flags=0):
+    """(GPU pattern, oracle) for a regex, cached."""
+    key = (regex, flags)
+    if key not in _P:
+        blob = nb.compile_to_bytes(regex, flags)
+        _P[key] = (nb.Pattern(blob, device=0), Oracle(blob))
+    return _P[key]
+
+
+def assert_batch_equal(regex, flags, data, offsets, cw=1, from_=None, modes=(0, 1, 2)):
+    pat, ora = pair(regex, flags)
+    for mode in modes:
+        got = pat.match_batch(mode, data, offsets, cw, from_ if mode == 2 else None)
+        exp = ora.match_batch(mode, data, offsets, cw, from_ if mode == 2 else None, threads=8)
+        for name, g, e in zip(("matched", "start", "end"), got, exp):
+            if e is None:
+                continue
+            if not np.array_equal(g, e):
+                bad = np.nonzero(g != e)[0]
+                i = int(bad[0])
+                o0, o1 = int(offsets[i]), int(offsets[i + 1])
+                raise AssertionError(f"{regex!r} flags={flags:#x} mode={mode} {name}: {len(bad)} of {len(e)} differ; first i={i} "
+                                     f"gpu={g[i]} oracle={e[i]} haystack={bytes(data[o0 * cw:o1 * cw])!r}")
+
+
+def test_native_library_is_the_one_loaded():
+    assert os.path.exists(_lib.LIB_PATH)
+    assert _lib.lib().ndl_device_count() >= 1
+    before = _lib.lib().ndl_kernel_launches()
+    pat, _ = pair("abc")
+    pat.match_batch(2, np.frombuffer(b"xxabcxx", dtype=np.uint8), np.array([0, 7], dtype=np.uint64))
+    assert _lib.lib().ndl_kernel_launches() > before
+
+
+def test_matches_txt_all_rows_on_gpu(golden_dir):
+    with open(os.path.join(golden_dir, "matches.json"), encoding="utf-8") as f:
+        rows = json.load(f)
+    bad = []
+    for r in rows:
+        fl = r["flags"] if r["flags"] is not None else r["java_random_flags"]
+        pat, ora = pair(r["pattern"], fl)
+        m = pat.matcher(r["haystack"])
+        found = m.find()
+        got = (found, m.start(), m.end())
+        exp = (r["matched"], r["start"], r["end"])
+        if got != exp:
+            bad.append((r["line"], r["pattern"], r["haystack"], hex(fl), got, exp))
+        # and the other two entry points agree with the oracle
+        assert pat.matcher(r["haystack"]).matches() == ora.matches(r["haystack"]), r
+        assert pat.matcher(r["haystack"]).containedIn() == ora.contained_in(r["haystack"]), r
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("regex,flags,match,fail,contained", kats.MATCH_FAIL, ids=[k[0][:30] for k in kats.MATCH_FAIL])
+def test_inline_match_fail_on_gpu(regex, flags, match, fail, contained):
+    pat, _ = pair(regex, flags)
+    for s in match:
+        m = pat.matcher(s)
+        assert m.matches() and m.containedIn(), s
+        assert m.find() and (m.start(), m.end()) == (0, len(s)), s
+    for s in fail:
+        assert not pat.matcher(s).containedIn() and not pat.matcher(s).matches(), s
+    for s in contained:
+        assert not pat.matcher(s).matches() and pat.matcher(s).containedIn(), s
+
+
+@pytest.mark.parametrize("regex,flags,hay,frm,exp", kats.FIND)
+def test_inline_find_on_gpu(regex, flags, hay, frm, exp):
+    pat, _ = pair(regex, flags)
+    m = pat.matcher(hay)
+    found = m.find(frm, len(hay))
+    assert (found, m.start(), m.end()) == exp
+
+
+@pytest.mark.parametrize("regex,flags,hay,exp", kats.FIND_ALL)
+def test_iterated_find_on_gpu(regex, flags, hay, exp):
+    pat, _ = pair(regex, flags)
+    assert list(nb.iter_find(pat, hay)) == exp
+    m = pat.matcher(hay)
+    while m.find():
+        pass
+    assert not m.find() and not m.find()  # findDoesntRollOver (DFACompilerTest.java:816-825)
+
+
+def test_c1_url_strings():
+    strings = workloads.c1_strings(1000)
+    data, offsets, cw = nb.pack_haystacks(strings)
+    assert_batch_equal(workloads.REGEX["c1"], 0, data, offsets, cw)
+    pat, _ = pair(workloads.REGEX["c1"])
+    m, s, e = pat.match_batch(2, data, offsets, cw)
+    for i, st in enumerate(strings):
+        assert bool(m[i]) == ("http://" in st and len(st) > st.index("http://") + 7)
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 1007, 1008, 1009, 4096, 200_003])
+def test_c2_ssn_fixed_lines(n):
+    data, offsets = workloads.c2_lines(n)
+    assert_batch_equal(workloads.REGEX["c2"], 0, data, offsets)
+    pat, _ = pair(workloads.REGEX["c2"])
+    m, s, e = pat.match_batch(2, data, offsets)
+    assert np.all((e - s)[m == 1] == 11)  # fixed-length pattern: start = end - 11
+
+
+@pytest.mark.parametrize("line_len", [16, 32, 64, 128, 48, 80, 256, 11, 1])
+def test_fixed_lines_all_lengths(line_len):
+    rng = np.random.default_rng(line_len)
+    n = 5000
+    alpha = np.frombuffer(b"0123456789-ab ", dtype=np.uint8)
+    data = alpha[rng.integers(0, len(alpha), size=n * line_len)]
+    offsets = np.arange(n + 1, dtype=np.uint64) * np.uint64(line_len)
+    for regex in (workloads.REGEX["c2"], r"[0-9]+", r"a*", r"(ab|a|b-)+", r"\d+-\d+"):
+        assert_batch_equal(regex, 0, data, offsets)
+
+
+def test_unaligned_base_and_sub_batches():
+    data, offsets = workloads.c2_lines(3000)
+    pat, ora = pair(workloads.REGEX["c2"])
+    # a batch that starts in the middle of the buffer (offsets[0] != 0)
+    sub = offsets[1000:2501]
+    got = pat.match_batch(2, data, sub)
+    exp = ora.match_batch(2, data, sub)
+    for g, e in zip(got, exp):
+        assert np.array_equal(g, e)
+    # a data pointer that is not 16-byte aligned
+    shifted = np.empty(len(data) + 5, dtype=np.uint8)
+    shifted[5:] = data
+    got = pat.match_batch(2, shifted[5:], offsets)
+    exp = ora.match_batch(2, data, offsets)
+    for g, e in zip(got, exp):
+        assert np.array_equal(g, e)
+
+
+@pytest.mark.parametrize("n", [1, 77, 50_000])
+def test_c3_email_ragged_lines(n):
+    data, offsets = workloads.c3_lines(n)
+    assert_batch_equal(workloads.REGEX["c3"], 0, data, offsets)
+
+
+def test_c4_256_state_dfa_batched():
+    data, offsets = workloads.c4_lines(20_000)
+    assert_batch_equal(workloads.REGEX["c4"], 0, data, offsets)
+    pat, _ = pair(workloads.REGEX["c4"])
+    assert pat.info.n_states[2] >= 256
+
+
+def test_c5_bmp_utf16_lines():
+    data, offsets = workloads.c5_lines(20_000)
+    assert_batch_equal(workloads.REGEX["c5"], 0, data, offsets, cw=2)
+
+
+def test_find_with_from_offsets():
+    data, offsets = workloads.c3_lines(5000)
+    rng = np.random.default_rng(5)
+    lens = (offsets[1:] - offsets[:-1]).astype(np.int64)
+    from_ = (rng.random(len(lens)) * (lens + 1)).astype(np.int32)
+    for regex in (workloads.REGEX["c3"], "a*", "[a-z]+", r"\d{2}"):
+        assert_batch_equal(regex, 0, data, offsets, from_=from_, modes=(2,))
+
+
+def test_empty_and_degenerate_batches():
+    pat, ora = pair("a*")
+    m, s, e = pat.match_batch(2, np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.uint64))
+    assert len(m) == 0
+    strings = ["", "", "a", "", "b", ""]
+    data, offsets, cw = nb.pack_haystacks(strings)
+    assert_batch_equal("a*", 0, data, offsets, cw)
+    assert_batch_equal("a+", 0, data, offsets, cw)
+    assert_batch_equal("", 0, data, offsets, cw)
+
+
+def test_reverse_scan_variants():
+    # table-driven reverse pass, single-char reverse scan (SherlockStreet snapshot), fixed length
+    rng = np.random.default_rng(9)
+    words = ["Sherlock", "Street", "Holmes", "Watson", " ", "x", "S", "Sh", "anywhere", "somewhere", "where", "\n"]
+    strings = ["".join(words[j] for j in rng.integers(0, len(words), int(rng.integers(0, 12)))) for _ in range(4000)]
+    data, offsets, cw = nb.pack_haystacks(strings)
+    for regex in ("Sherlock|Street", "[Ss]herlock", "anywhere|somewhere", "Holmes.{1,10}Watson|Watson.{1,10}Holmes",
+                  "([Ss]herlock)|([Hh]olmes)", "Sherlock|Holmes|Watson|Irene|Adler|John|Baker", "S.*e", "d|[a-c]x"):
+        assert_batch_equal(regex, 0, data, offsets, cw)
+    # same data as fixed 64-byte lines so the shared-memory kernel's reverse paths run too
+    blob = "".join(strings).encode("latin-1")
+    n = len(blob) // 64
+    fixed = np.frombuffer(blob[:n * 64], dtype=np.uint8)
+    off64 = np.arange(n + 1, dtype=np.uint64) * np.uint64(64)
+    for regex in ("Sherlock|Street", "anywhere|somewhere", "([Ss]herlock)|([Hh]olmes)", "S.*e", "[a-z]+"):
+        assert_batch_equal(regex, 0, fixed, off64)
+
+
+def test_flags_on_gpu():
+    strings = ["Sam", "SAMWISE", "samwise", "abc\nabc", "ΓΔΘ γδθ", "x"]
+    data, offsets, cw = nb.pack_haystacks(strings)
+    for regex, fl in (("sam|samwise", nb.CASE_INSENSITIVE), ("sam|samwise", nb.LEFTMOST_LONGEST | nb.CASE_INSENSITIVE),
+                      (".{5}", nb.DOTALL), (".{5}", 0), ("[Γ-Θ]+", nb.CASE_INSENSITIVE | nb.UNICODE_CASE),
+                      (r"\w+", nb.UNICODE_CHARACTER_CLASS), (r"\w+", 0)):
+        assert_batch_equal(regex, fl, data, offsets, cw)
+
+
+def test_large_table_pattern_uses_generic_path():
+    # 309-state search DFA (HolmesNearWatson snapshot): too big for the replicated shared-memory image
+    data, offsets = workloads.c2_lines(2000)
+    text = np.frombuffer(("Holmes and then Watson " * 6000).encode()[:2000 * 64], dtype=np.uint8)
+    assert_batch_equal("Holmes.{1,10}Watson|Watson.{1,10}Holmes", 0, text, offsets)
+
+
+def test_device_memory_entry_point():
+    torch = pytest.importorskip("torch")
+    data, offsets = workloads.c2_lines(100_000)
+    pat, ora = pair(workloads.REGEX["c2"])
+    d = torch.from_numpy(data).cuda()
+    o = torch.from_numpy(offsets.view(np.int64)).cuda()
+    n = len(offsets) - 1
+    matched = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    start = torch.zeros(n, dtype=torch.int32, device="cuda")
+    end = torch.zeros(n, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    pat.match_batch_ptrs(2, d.data_ptr(), o.data_ptr(), n, 1, matched.data_ptr(), start.data_ptr(), end.data_ptr(), stream=stream)
+    torch.cuda.synchronize()
+    em, es, ee = ora.match_batch(2, data, offsets, threads=8)
+    assert np.array_equal(matched.cpu().numpy(), em)
+    assert np.array_equal(start.cpu().numpy(), es)
+    assert np.array_equal(end.cpu().numpy(), ee)
+
+
+def test_full_size_properties_c2():
+    """BASELINE config 2 at full size (10 M x 64 B): too big for the oracle in seconds, so check
+    size-independent properties: every planted SSN is found, end - start == 11, the matched span
+    re-matches, and an oracle spot-check on a random sample of lines."""
+    n = 10_000_000
+    data, offsets = workloads.c2_lines(n)
+    pat, ora = pair(workloads.REGEX["c2"])
+    m, s, e = pat.match_batch(2, data, offsets)
+    assert 0.25 * n * 0.98 < m.sum()  # >= the planted fraction (random text adds a few more)
+    assert np.all((e - s)[m == 1] == 11) and np.all(s[m == 0] == -1) and np.all(e[m == 0] == -1)
+    hit = np.nonzero(m)[0]
+    starts = offsets[hit].astype(np.int64) + s[hit]
+    span = data[starts[:, None] + np.arange(11)[None, :]]
+    assert np.all(span[:, 3] == ord("-")) and np.all(span[:, 6] == ord("-"))
+    digits = np.delete(span, [3, 6], axis=1)
+    assert np.all((digits >= ord("0")) & (digits <= ord("9")))
+    rng = np.random.default_rng(1)
+    sample = np.sort(rng.choice(n, size=200_000, replace=False))
+    sub_off = np.zeros(len(sample) + 1, dtype=np.uint64)
+    sub_off[1:] = np.cumsum(np.full(len(sample), 64, dtype=np.uint64))
+    sub = data.reshape(n, 64)[sample].reshape(-1)
+    em, es, ee = ora.match_batch(2, sub, sub_off, threads=8)
+    assert np.array_equal(m[sample], em) and np.array_equal(s[sample], es) and np.array_equal(e[sample], ee)
+    # matches()/containedIn() agree with find() where they must
+    mc, _, _ = pat.match_batch(1, data, offsets)
+    assert np.array_equal(mc, m)
