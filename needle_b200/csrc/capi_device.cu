@@ -33,7 +33,6 @@ struct DeviceTableStorage {
   uint16_t* cmap = nullptr;
   uint16_t* trans = nullptr;
   uint8_t* accept = nullptr;
-  Lines8Image fast;  // bank-replicated image for the byte-input kernels (may be unavailable)
   DevTable view() const {
     DevTable v;
     v.cmap = cmap;
@@ -140,12 +139,8 @@ static int launch_batch(ndl_pattern* p, const BatchParams& bp, int char_width, u
     lp.g = bp;
     lp.image = img.dev;
     lp.trans_bytes = img.trans_bytes;
-    lp.fwd_root = img.fwd_root;
-    lp.bwd_root = img.bwd_root;
-    lp.fwd_repl = img.fwd_repl;
-    lp.bwd_repl = img.bwd_repl;
-    lp.use_bwd_table = img.has_bwd ? 1 : 0;
-    uint64_t max_tiles = (bp.n + 511) / 512;  // at least 512 lines per tile for every supported L
+    lp.root_entry = img.root_entry;
+    uint64_t max_tiles = (bp.n + 1023) / 1024;  // a CTA's 32 warps take 32 lines each per round
     int blocks = static_cast<int>(max_tiles < static_cast<uint64_t>(p->sm_count) ? max_tiles : p->sm_count);
     lines8_kernel<<<blocks, kL8Threads, kL8DynSmem, stream>>>(lp);
     g_launches.fetch_add(1);
@@ -211,7 +206,6 @@ int ndl_pattern_create(const uint8_t* blob, size_t blob_len, int device, ndl_pat
   for (int k = 0; k < 4; k++) {
     p->tables[k].host = build_device_table(p->cp, k);
     int rc = upload_table(p->tables[k]);
-    if (rc == NDL_OK) lines8_build(p->tables[k].host, p->tables[k].fast);
     if (rc != NDL_OK) {
       free_pattern(p);
       return rc;
@@ -220,12 +214,9 @@ int ndl_pattern_create(const uint8_t* blob, size_t blob_len, int device, ndl_pat
   // shared-memory images of the byte-input kernel, one per mode
   cudaError_t ae = cudaFuncSetAttribute(lines8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kL8DynSmem);
   for (int mode = 0; mode < 3 && ae == cudaSuccess; mode++) {
-    const Lines8Image& fwd = p->tables[mode == NDL_MODE_FIND ? kForwards : mode].fast;
-    const Lines8Image* bwd = (mode == NDL_MODE_FIND && p->cp.reverse_mode == kReverseTable) ? &p->tables[kBackwards].fast : nullptr;
     std::vector<uint8_t> img;
     Lines8Blob& b = p->l8[mode];
-    bool ok = lines8_layout(fwd, bwd, img, b);
-    if (!ok && bwd) ok = lines8_layout(fwd, nullptr, img, b);  // reverse pass then walks the global tables
+    const bool ok = lines8_layout(p->tables[mode == NDL_MODE_FIND ? kForwards : mode].host, img, b);
     if (!ok) continue;
     if (cudaMalloc(&b.dev, img.size()) != cudaSuccess ||
         cudaMemcpy(b.dev, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
