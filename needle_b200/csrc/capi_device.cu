@@ -133,7 +133,7 @@ static int ensure_workspace(Workspace& ws, size_t data_bytes, uint64_t n, bool w
 static int launch_batch(ndl_pattern* p, const BatchParams& bp, int char_width, uint64_t total_chars, cudaStream_t stream) {
   if (bp.n == 0) return NDL_OK;
   (void)total_chars;
-  if (char_width == 1 && bp.from == nullptr && p->l8[bp.mode].ok && bp.n >= 2) {
+  if (char_width == 1 && bp.from == nullptr && p->l8[bp.mode].ok && bp.n >= 2 && bp.n < (1ull << 31)) {
     const Lines8Blob& img = p->l8[bp.mode];
     Lines8Params lp;
     lp.g = bp;

@@ -215,13 +215,139 @@ __device__ __forceinline__ void l8_slow_line(const BatchParams& g, uint64_t i) {
   }
 }
 
+// The walk of one regular warp tile, specialised on the line length (L = 16 << LOG2CPL bytes).
+template <int LOG2CPL>
+struct L8Geom {
+  static constexpr uint32_t kCpl = 1u << LOG2CPL;                                 // 16-byte chunks per line
+  static constexpr uint32_t kL = 16u * kCpl;                                      // bytes per line
+  static constexpr uint32_t kTileLines = (kL8WarpBuf / kL) < 32u ? (kL8WarpBuf / kL) : 32u;
+  static constexpr uint32_t kCopies = kTileLines * kCpl / 32u;                    // cp.async per lane per tile
+};
+
+template <int LOG2CPL>
+__device__ __forceinline__ void l8_run(const Lines8Params& p, const uint32_t buf0, const uint32_t buf1, const uint32_t lane,
+                                       const uint32_t warp_global, const uint32_t n_warps) {
+  using G = L8Geom<LOG2CPL>;
+  const BatchParams& g = p.g;
+  const uint8_t* const data = static_cast<const uint8_t*>(g.data);
+  const uint32_t n = static_cast<uint32_t>(g.n);  // the host only takes this path for n < 2^31
+  const uint32_t n_full = n / G::kTileLines;
+  const bool active = lane < G::kTileLines;
+
+  // per-lane constants: where this lane's copies land, and where its own line's chunks are read from
+  uint32_t dst_off[G::kCopies];
+#pragma unroll
+  for (uint32_t k = 0; k < G::kCopies; k++) {
+    const uint32_t c = lane + 32 * k;
+    dst_off[k] = l8_slot(c >> LOG2CPL, c & (G::kCpl - 1), LOG2CPL) << 4;
+  }
+  const uint32_t sel_a = 0x00010000u | (lane * 4);
+  const uint32_t sel_b = sel_a | 0x80u;
+  const uint32_t lane_line = active ? lane : 0;
+
+  // offsets of line (tile * kTileLines + lane) and the next one
+  auto load_offsets = [&](uint32_t tile, uint64_t& o0, uint64_t& o1) {
+    const uint32_t i = tile * G::kTileLines + lane_line;
+    o0 = g.offsets[i];
+    o1 = g.offsets[i + 1];
+  };
+  // Issue the copies of a tile whose offsets are (o0, o1); returns whether the tile is regular.
+  auto stage = [&](uint64_t o0, uint64_t o1, uint32_t buf) -> bool {
+    const uint64_t tile_off = o0 - static_cast<uint64_t>(lane_line) * G::kL;  // same on every lane iff regular
+    const uint8_t* src = data + tile_off;
+    const bool ok = (o1 - o0 == G::kL) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    const bool regular = __all_sync(0xffffffffu, ok) != 0;
+    if (regular) {
+      src += lane * 16;
+#pragma unroll
+      for (uint32_t k = 0; k < G::kCopies; k++) cp_async16(buf + dst_off[k], src + 512 * k);
+    }
+    cp_async_commit();
+    return regular;
+  };
+
+  uint32_t t = warp_global;
+  uint32_t cur = buf0, nxt = buf1;
+  bool regular = false;
+  uint64_t a0 = 0, a1 = 0;  // offsets of the tile after the current one
+  if (t < n_full) {
+    load_offsets(t, a0, a1);
+    regular = stage(a0, a1, cur);
+    if (t + n_warps < n_full) load_offsets(t + n_warps, a0, a1);
+  }
+  for (; t < n_full; t += n_warps) {
+    bool regular_next = false;
+    if (t + n_warps < n_full) {
+      regular_next = stage(a0, a1, nxt);
+      if (t + 2 * n_warps < n_full) load_offsets(t + 2 * n_warps, a0, a1);  // prefetch: consumed next iteration
+    } else {
+      cp_async_commit();
+    }
+    cp_async_wait<1>();
+    __syncwarp();
+
+    const uint32_t i = t * G::kTileLines + lane;
+    if (regular) {
+      if (active) {
+        uint32_t e = p.root_entry;
+        int32_t last = g.fwd.root_accepting ? 0 : -1;
+        uint32_t mask = 0;
+#pragma unroll
+        for (uint32_t c = 0; c < G::kCpl; c++) {
+          const uint4 w = lds_data16(cur + (l8_slot(lane, c, LOG2CPL) << 4));
+          l8_word(w.x, sel_a, sel_b, e, mask);
+          l8_word(w.y, sel_a, sel_b, e, mask);
+          l8_word(w.z, sel_a, sel_b, e, mask);
+          l8_word(w.w, sel_a, sel_b, e, mask);
+          if ((c & 1) || c + 1 == G::kCpl) {  // mask holds <= 32 chars; bit 0 = the most recent one
+            const int32_t cand = static_cast<int32_t>((c + 1) * 16 + 1) - __ffs(mask);
+            last = mask ? cand : last;
+            mask = 0;
+          }
+        }
+        if (g.mode == 0) {
+          bool m = (e & 0x40000000u) != 0;
+          if (g.min_length > 4 && static_cast<uint32_t>(g.min_length) > G::kL) m = false;  // DFAMethodComponents.java:75-93
+          if (g.max_length != -1 && G::kL > static_cast<uint32_t>(g.max_length)) m = false;
+          g.matched[i] = m;
+        } else if (g.mode == 1) {
+          g.matched[i] = (e & 0x40000000u) != 0;
+        } else {
+          int32_t st = -1;
+          if (last != -1) {
+            if (g.reverse_mode == 2)  // start = end - minLength (DFAClassBuilder.java:640-646)
+              st = last - g.min_length;
+            else  // indexBackwards / single-char reverse scan (:529-614) over the global tables
+              st = static_cast<int32_t>(dev_index_backwards<uint8_t>(g, data + g.offsets[i], last - 1, 0, 0x7fffffff));
+          }
+          g.matched[i] = last != -1;
+          g.start[i] = st;
+          g.end[i] = last;
+        }
+      }
+    } else if (active) {
+      l8_slow_line(g, i);
+    }
+    __syncwarp();  // every lane is done with `cur` before the stage after next overwrites it
+    regular = regular_next;
+    const uint32_t tmp = cur;
+    cur = nxt;
+    nxt = tmp;
+  }
+  cp_async_wait<0>();
+  // the partial last tile
+  if (warp_global == 0) {
+    const uint32_t i = n_full * G::kTileLines + lane;
+    if (i < n) l8_slow_line(g, i);
+  }
+}
+
 __global__ void __launch_bounds__(kL8Threads, 1) lines8_kernel(const Lines8Params p) {
   extern __shared__ __align__(128) uint8_t l8_dyn_smem[];
   const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(l8_dyn_smem));
   const uint32_t tid = threadIdx.x;
   const uint32_t lane = tid & 31, warp = tid >> 5;
   const BatchParams& g = p.g;
-  const uint8_t* const data = static_cast<const uint8_t*>(g.data);
 
   // set-0 buffers fill the space between the start of dynamic shared memory and the class map; the ones
   // that do not fit (one, when the base is 0x400) live in the spill area
@@ -245,107 +371,24 @@ __global__ void __launch_bounds__(kL8Threads, 1) lines8_kernel(const Lines8Param
     tma_bulk_g2s(kL8AbsTrans, p.image + kL8CmapBytes, p.trans_bytes, kL8AbsBar);
   }
 
-  // --- line geometry: L from the first two offsets (uniform)
+  // --- line geometry: L from the first two offsets (uniform); every tile re-checks its own lines
   const uint64_t L64 = g.offsets[1] - g.offsets[0];
   int log2cpl = -1;
   if (warp_ok && L64 >= 16 && L64 <= 256 && (L64 & (L64 - 1)) == 0) log2cpl = 31 - __clz(static_cast<uint32_t>(L64)) - 4;
-  const uint32_t L = static_cast<uint32_t>(L64);
-  const uint32_t tile_lines = (log2cpl < 0) ? 32u : min(32u, kL8WarpBuf / L);
-  const uint64_t n_tiles = (g.n + tile_lines - 1) / tile_lines;
-  const uint64_t tile_step = static_cast<uint64_t>(gridDim.x) * kL8Warps;
-
-  // Stage warp tile `t` into `buf`; returns (warp-uniformly) whether the tile is regular.
-  auto stage = [&](uint64_t t, uint32_t buf) -> bool {
-    const uint64_t first = t * tile_lines;
-    const uint64_t i = first + lane;
-    int ok = log2cpl >= 0;
-    uint64_t o0 = 0;
-    if (ok && lane < tile_lines && i < g.n) {
-      o0 = g.offsets[i];
-      ok = (g.offsets[i + 1] - o0 == L);
-    }
-    const uint64_t tile_off = __shfl_sync(0xffffffffu, o0, 0);
-    ok = ok && ((reinterpret_cast<uintptr_t>(data) + tile_off) & 15) == 0;
-    const bool regular = __all_sync(0xffffffffu, ok) != 0;
-    if (regular) {
-      const uint32_t lines_here = static_cast<uint32_t>(min(static_cast<uint64_t>(tile_lines), g.n - first));
-      const uint32_t n_chunks = lines_here << log2cpl;
-      const uint8_t* src = data + tile_off + lane * 16;
-#pragma unroll 4
-      for (uint32_t c = lane; c < n_chunks; c += 32, src += 512) {
-        const uint32_t line = c >> log2cpl, ch = c & ((1u << log2cpl) - 1);
-        cp_async16(buf + (l8_slot(line, ch, log2cpl) << 4), src);
-      }
-    }
-    cp_async_commit();
-    return regular;
-  };
-
-  uint64_t t = static_cast<uint64_t>(blockIdx.x) * kL8Warps + warp;
-  bool regular = false;
-  uint32_t cur = buf0, nxt = buf1;
-  if (t < n_tiles) regular = stage(t, cur);
   if (layout_ok) mbar_wait(kL8AbsBar, 0);  // table image has landed
 
-  const uint32_t sel_a = 0x00010000u | (lane * 4);
-  const uint32_t sel_b = sel_a | 0x80u;
-
-  for (; t < n_tiles; t += tile_step) {
-    const uint64_t t_next = t + tile_step;
-    bool regular_next = false;
-    if (t_next < n_tiles) regular_next = stage(t_next, nxt);
-    else cp_async_commit();
-    cp_async_wait<1>();
-    __syncwarp();
-
-    const uint64_t i = t * tile_lines + lane;
-    if (lane < tile_lines && i < g.n) {
-      if (regular) {
-        uint32_t e = p.root_entry;
-        int32_t last = g.fwd.root_accepting ? 0 : -1;
-        const uint32_t cpl = 1u << log2cpl;
-        uint32_t mask = 0;
-        for (uint32_t c = 0; c < cpl; c++) {
-          const uint4 w = lds_data16(cur + (l8_slot(lane, c, log2cpl) << 4));
-          l8_word(w.x, sel_a, sel_b, e, mask);
-          l8_word(w.y, sel_a, sel_b, e, mask);
-          l8_word(w.z, sel_a, sel_b, e, mask);
-          l8_word(w.w, sel_a, sel_b, e, mask);
-          if ((c & 1) || c + 1 == cpl) {  // mask holds <= 32 chars; bit 0 = the most recent one
-            if (mask) last = static_cast<int32_t>((c + 1) * 16) - (__ffs(mask) - 1);
-            mask = 0;
-          }
-        }
-        if (g.mode == 0) {
-          bool m = (e & 0x40000000u) != 0;
-          if (g.min_length > 4 && static_cast<uint32_t>(g.min_length) > L) m = false;  // DFAMethodComponents.java:75-93
-          if (g.max_length != -1 && L > static_cast<uint32_t>(g.max_length)) m = false;
-          g.matched[i] = m;
-        } else if (g.mode == 1) {
-          g.matched[i] = (e & 0x40000000u) != 0;
-        } else {
-          int32_t st = -1;
-          if (last != -1) {
-            if (g.reverse_mode == 2)  // start = end - minLength (DFAClassBuilder.java:640-646)
-              st = last - g.min_length;
-            else  // indexBackwards / single-char reverse scan (:529-614) over the global tables
-              st = static_cast<int32_t>(dev_index_backwards<uint8_t>(g, data + g.offsets[i], last - 1, 0, 0x7fffffff));
-          }
-          g.matched[i] = last != -1;
-          g.start[i] = st;
-          g.end[i] = last;
-        }
-      } else {
-        l8_slow_line(g, i);
-      }
-    }
-    __syncwarp();  // every lane is done with `cur` before the stage after next overwrites it
-    regular = regular_next;
-    const uint32_t tmp = cur;
-    cur = nxt;
-    nxt = tmp;
+  const uint32_t warp_global = blockIdx.x * kL8Warps + warp;
+  const uint32_t n_warps = gridDim.x * kL8Warps;
+  switch (log2cpl) {
+    case 0: l8_run<0>(p, buf0, buf1, lane, warp_global, n_warps); break;
+    case 1: l8_run<1>(p, buf0, buf1, lane, warp_global, n_warps); break;
+    case 2: l8_run<2>(p, buf0, buf1, lane, warp_global, n_warps); break;
+    case 3: l8_run<3>(p, buf0, buf1, lane, warp_global, n_warps); break;
+    case 4: l8_run<4>(p, buf0, buf1, lane, warp_global, n_warps); break;
+    default:
+      // no shared-memory fast path for this geometry: generic walk, one line per thread
+      for (uint64_t i = static_cast<uint64_t>(warp_global) * 32 + lane; i < g.n; i += static_cast<uint64_t>(n_warps) * 32) l8_slow_line(g, i);
   }
-  cp_async_wait<0>();
 }
 
 }  // namespace ndl
