@@ -161,18 +161,10 @@ def run_ours(args, rank, local_rank, world):
     n = args.lines or default_lines
 
     # regex -> table blob on rank 0; ONE NCCL broadcast of the blob; every rank uploads its own device image
-    if rank == 0:
-        blob = nb.compile_to_bytes(regex, 0)
-        size = torch.tensor([len(blob)], dtype=torch.int64, device=dev)
-    else:
-        blob, size = None, torch.zeros(1, dtype=torch.int64, device=dev)
+    blob = nb.compile_to_bytes(regex, 0) if rank == 0 else None
     if dist:
-        dist.broadcast(size, 0)
-        buf = torch.empty(int(size.item()), dtype=torch.uint8, device=dev)
-        if rank == 0:
-            buf.copy_(torch.frombuffer(bytearray(blob), dtype=torch.uint8))
-        dist.broadcast(buf, 0)
-        blob = bytes(buf.cpu().numpy().tobytes())
+        from needle_b200.sharding import broadcast_blob
+        blob = broadcast_blob(blob, src=0, device=dev)
     pat = nb.Pattern(blob, device=local_rank)
 
     # this rank's shard of the job: its own n lines (weak scaling), seeded by rank

@@ -1,0 +1,66 @@
+package com.justinblank.strings.gpu;
+
+import com.justinblank.strings.Matcher;
+import com.justinblank.strings.Pattern;
+
+import java.nio.ByteBuffer;
+import java.nio.ByteOrder;
+
+/**
+ * {@link Pattern} backed by an {@code ndl_pattern*}.  Stateless and shareable between threads, like the
+ * class the reference generates (DFACompiler.java:96-111).  Adds the one call a GPU needs: a batch.
+ */
+public final class GpuPattern implements Pattern, AutoCloseable {
+
+    final long handle;          // ndl_pattern*
+    private final byte[] blob;
+
+    public GpuPattern(byte[] blob, int device) {
+        this.blob = blob;
+        this.handle = NeedleNative.patternCreate(blob, device);
+    }
+
+    @Override
+    public Matcher matcher(String s) {
+        return new GpuMatcher(this, s);
+    }
+
+    /** Result of one batch: matched[i], start[i], end[i] exactly as Matcher.find()/start()/end() would give. */
+    public static final class BatchResult {
+        public final byte[] matched;
+        public final int[] start;
+        public final int[] end;
+
+        BatchResult(int n) {
+            matched = new byte[n];
+            start = new int[n];
+            end = new int[n];
+        }
+    }
+
+    /**
+     * Run {@code mode} (0 matches, 1 containedIn, 2 find) over n haystacks packed in a direct buffer.
+     *
+     * @param data      direct ByteBuffer with the packed chars (charWidth 1 = Latin-1 bytes, 2 = UTF-16LE)
+     * @param offsets   n+1 offsets in chars (direct LongBuffer backing store)
+     */
+    public BatchResult matchBatch(int mode, ByteBuffer data, ByteBuffer offsets, int n, int charWidth) {
+        BatchResult r = new BatchResult(n);
+        NeedleNative.matchBatch(handle, mode, data, offsets.order(ByteOrder.LITTLE_ENDIAN), n, charWidth, r.matched, r.start, r.end);
+        return r;
+    }
+
+    /** Convenience: find() on every string. */
+    public BatchResult findAll(String[] haystacks) {
+        return NeedleNative.findAllStrings(handle, haystacks);
+    }
+
+    public byte[] blob() {
+        return blob.clone();
+    }
+
+    @Override
+    public void close() {
+        NeedleNative.patternDestroy(handle);
+    }
+}
