@@ -342,6 +342,137 @@ __device__ __forceinline__ void l8_run(const Lines8Params& p, const uint32_t buf
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Ragged lines: a warp tile is the longest run of <= 32 consecutive lines whose bytes (from the 16-byte
+// boundary below the first line) fit in the warp's 2 KB buffer.  Chunks are stored XOR-swizzled by
+// (chunk >> 3) so that lines of about 64 bytes still read conflict free.  A lane reads its line as
+// aligned 16-byte chunks and realigns them in registers (word select by the start offset, then funnel
+// shifts).  The walk simply runs over whole 16-byte windows: chars past the end of a line only produce
+// accept bits past the end, which are shifted out, so no per-char bounds test is needed.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t l8_rslot(uint32_t c) { return (c ^ ((c >> 3) & 7)) << 4; }
+
+__device__ __forceinline__ void l8_run_ragged(const Lines8Params& p, const uint32_t buf0, const uint32_t buf1, const uint32_t lane,
+                                              const uint32_t warp_global, const uint32_t n_warps) {
+  const BatchParams& g = p.g;
+  const uint8_t* const data = static_cast<const uint8_t*>(g.data);
+  const uint32_t n = static_cast<uint32_t>(g.n);
+  const uint32_t per_warp = (n + n_warps - 1) / n_warps;
+  const uint32_t lo = min(n, warp_global * per_warp), hi = min(n, lo + per_warp);
+  const uint32_t sel_a = 0x00010000u | (lane * 4);
+  const uint32_t sel_b = sel_a | 0x80u;
+  constexpr uint32_t kCap = kL8WarpBuf - 16;  // the last 16 bytes stay free for the window that runs past the tile
+
+  struct Plan {
+    uint32_t count;   // lines in the tile (0: the first line alone does not fit)
+    uint32_t start;   // this lane's line: first byte, relative to the tile buffer
+    uint32_t len;     // this lane's line length
+  };
+  // Plan the tile that starts at line c and issue its copies into buf.
+  auto plan_and_stage = [&](uint32_t c, uint32_t buf) -> Plan {
+    Plan pl;
+    pl.count = 0; pl.start = 0; pl.len = 0;
+    if (c < hi) {
+      const uint64_t s0 = g.offsets[c];
+      const uint32_t idx = min(c + lane + 1, hi);
+      const uint64_t e = g.offsets[idx];
+      const uint32_t slack = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(data) + s0) & 15u;
+      const uint64_t rel_end = e - s0 + slack;  // end of this lane's line relative to the tile buffer
+      const bool fits = (c + lane < hi) && rel_end <= kCap;
+      const uint32_t ballot = __ballot_sync(0xffffffffu, fits);
+      pl.count = __popc(ballot);  // offsets are non-decreasing, so `fits` is a prefix
+      const uint32_t end32 = static_cast<uint32_t>(rel_end);
+      uint32_t prev = __shfl_up_sync(0xffffffffu, end32, 1);
+      if (lane == 0) prev = slack;
+      pl.start = prev;
+      pl.len = end32 - prev;
+      if (pl.count) {
+        const uint32_t total = __shfl_sync(0xffffffffu, end32, pl.count - 1);
+        const uint32_t n_chunks = (total + 15) >> 4;
+        const uint8_t* src = data + s0 - slack;
+        for (uint32_t j = lane; j < n_chunks; j += 32) cp_async16(buf + l8_rslot(j), src + (static_cast<uint64_t>(j) << 4));
+      }
+    }
+    cp_async_commit();
+    return pl;
+  };
+
+  uint32_t c = lo;
+  uint32_t cur = buf0, nxt = buf1;
+  Plan pl = plan_and_stage(c, cur);
+  while (c < hi) {
+    if (pl.count == 0) {  // a line longer than the buffer: walk it straight from global memory
+      cp_async_wait<0>();
+      if (lane == 0) l8_slow_line(g, c);
+      c += 1;
+      __syncwarp();
+      pl = plan_and_stage(c, cur);
+      continue;
+    }
+    const uint32_t c_next = c + pl.count;
+    const Plan pl_next = plan_and_stage(c_next, nxt);
+    cp_async_wait<1>();
+    __syncwarp();
+
+    if (lane < pl.count) {
+      const uint32_t i = c + lane;
+      const uint32_t len = pl.len;
+      const uint32_t sh = pl.start & 15u;
+      const uint32_t c0 = pl.start >> 4;
+      const bool q1 = (sh & 4u) != 0, q2 = (sh & 8u) != 0;
+      const uint32_t r8 = (sh & 3u) * 8u;
+      uint32_t e = p.root_entry;
+      int32_t last = g.fwd.root_accepting ? 0 : -1;
+      uint32_t tail_bit = g.fwd.root_accepting ? 1u : 0u;  // accept flag exactly at the end of the line (matches())
+      uint4 x = lds_data16(cur + l8_rslot(c0));
+      for (uint32_t pos = 0; pos < len; pos += 16) {
+        const uint4 y = lds_data16(cur + l8_rslot(c0 + (pos >> 4) + 1));
+        // word select by the word part of the start offset, then funnel shift by its byte part
+        const uint32_t a0 = q2 ? x.z : x.x, a1 = q2 ? x.w : x.y, a2 = q2 ? y.x : x.z, a3 = q2 ? y.y : x.w;
+        const uint32_t a4 = q2 ? y.z : y.x, a5 = q2 ? y.w : y.y;
+        const uint32_t w0 = q1 ? a1 : a0, w1 = q1 ? a2 : a1, w2 = q1 ? a3 : a2, w3 = q1 ? a4 : a3, w4 = q1 ? a5 : a4;
+        uint32_t mask = 0;
+        l8_word(__funnelshift_r(w0, w1, r8), sel_a, sel_b, e, mask);
+        l8_word(__funnelshift_r(w1, w2, r8), sel_a, sel_b, e, mask);
+        l8_word(__funnelshift_r(w2, w3, r8), sel_a, sel_b, e, mask);
+        l8_word(__funnelshift_r(w3, w4, r8), sel_a, sel_b, e, mask);
+        const uint32_t valid = min(16u, len - pos);
+        mask >>= (16u - valid);  // drop the accept bits of chars past the end of the line
+        const int32_t cand = static_cast<int32_t>(pos + valid + 1) - __ffs(mask);
+        last = mask ? cand : last;
+        tail_bit = mask & 1u;
+        x = y;
+      }
+      if (g.mode == 0) {
+        bool m = tail_bit != 0;
+        if (g.min_length > 4 && static_cast<uint32_t>(g.min_length) > len) m = false;  // DFAMethodComponents.java:75-93
+        if (g.max_length != -1 && len > static_cast<uint32_t>(g.max_length)) m = false;
+        g.matched[i] = m;
+      } else if (g.mode == 1) {
+        g.matched[i] = last != -1;  // accepting rows of the containedIn automaton are absorbing
+      } else {
+        int32_t st = -1;
+        if (last != -1) {
+          if (g.reverse_mode == 2)
+            st = last - g.min_length;
+          else
+            st = static_cast<int32_t>(dev_index_backwards<uint8_t>(g, data + g.offsets[i], last - 1, 0, 0x7fffffff));
+        }
+        g.matched[i] = last != -1;
+        g.start[i] = st;
+        g.end[i] = last;
+      }
+    }
+    __syncwarp();
+    c = c_next;
+    pl = pl_next;
+    const uint32_t tmp = cur;
+    cur = nxt;
+    nxt = tmp;
+  }
+  cp_async_wait<0>();
+}
+
 __global__ void __launch_bounds__(kL8Threads, 1) lines8_kernel(const Lines8Params p) {
   extern __shared__ __align__(128) uint8_t l8_dyn_smem[];
   const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(l8_dyn_smem));
@@ -374,20 +505,30 @@ __global__ void __launch_bounds__(kL8Threads, 1) lines8_kernel(const Lines8Param
   // --- line geometry: L from the first two offsets (uniform); every tile re-checks its own lines
   const uint64_t L64 = g.offsets[1] - g.offsets[0];
   int log2cpl = -1;
-  if (warp_ok && L64 >= 16 && L64 <= 256 && (L64 & (L64 - 1)) == 0) log2cpl = 31 - __clz(static_cast<uint32_t>(L64)) - 4;
+  if (L64 >= 16 && L64 <= 256 && (L64 & (L64 - 1)) == 0) log2cpl = 31 - __clz(static_cast<uint32_t>(L64)) - 4;
   if (layout_ok) mbar_wait(kL8AbsBar, 0);  // table image has landed
 
   const uint32_t warp_global = blockIdx.x * kL8Warps + warp;
   const uint32_t n_warps = gridDim.x * kL8Warps;
+  // The fixed-length path is taken when the batch starts with 33 equally spaced offsets of a supported
+  // length (its tiles still re-check themselves); everything else goes down the ragged path.
+  if (log2cpl >= 0) {
+    const uint32_t probe = static_cast<uint32_t>(min(static_cast<uint64_t>(lane) + 1, g.n - 1));
+    const bool same = g.offsets[probe + 1] - g.offsets[probe] == L64;
+    if (!__all_sync(0xffffffffu, same)) log2cpl = -1;
+  }
+  if (!warp_ok) {
+    // no room for this warp's buffers (unexpected shared-memory base): generic walk, one line per thread
+    for (uint64_t i = static_cast<uint64_t>(warp_global) * 32 + lane; i < g.n; i += static_cast<uint64_t>(n_warps) * 32) l8_slow_line(g, i);
+    return;
+  }
   switch (log2cpl) {
     case 0: l8_run<0>(p, buf0, buf1, lane, warp_global, n_warps); break;
     case 1: l8_run<1>(p, buf0, buf1, lane, warp_global, n_warps); break;
     case 2: l8_run<2>(p, buf0, buf1, lane, warp_global, n_warps); break;
     case 3: l8_run<3>(p, buf0, buf1, lane, warp_global, n_warps); break;
     case 4: l8_run<4>(p, buf0, buf1, lane, warp_global, n_warps); break;
-    default:
-      // no shared-memory fast path for this geometry: generic walk, one line per thread
-      for (uint64_t i = static_cast<uint64_t>(warp_global) * 32 + lane; i < g.n; i += static_cast<uint64_t>(n_warps) * 32) l8_slow_line(g, i);
+    default: l8_run_ragged(p, buf0, buf1, lane, warp_global, n_warps); break;
   }
 }
 
