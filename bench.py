@@ -277,6 +277,77 @@ def run_ours(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def run_long(args, rank, local_rank, world):
+    """BASELINE configs[3]: 256-state DFA over ONE 8 GiB haystack, find() start/end offsets (ndl_find_long).
+    The buffer is {a,b} noise with the only match in its last 9 bytes, so the whole buffer must be scanned."""
+    import torch
+
+    import needle_b200 as nb
+    from needle_b200 import _lib
+
+    if world != 1:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "unavailable": "c4long: the multi-GPU exchange for one haystack is not built; run with --gpus 1"}))
+        return
+    torch.cuda.set_device(local_rank)
+    regex = workloads.REGEX["c4"]
+    n = args.lines or (8 << 30)
+    blob = nb.compile_to_bytes(regex, 0)
+    pat = nb.Pattern(blob, device=local_rank)
+    g = torch.Generator(device="cuda")
+    g.manual_seed(0x5EED0004)
+    data = torch.randint(ord("a"), ord("b") + 1, (n,), dtype=torch.uint8, device="cuda", generator=g)
+    data[n - 9:] = torch.tensor(list(b"abababbac"), dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def step():
+        return pat.find_long_ptrs(data.data_ptr(), n, 1, 0, nb.MEM_DEVICE, stream.cuda_stream)
+
+    for _ in range(args.warmup):
+        res = step()
+    if res != (True, n - 9, n):
+        raise SystemExit(f"bench: ndl_find_long returned {res}, expected {(True, n - 9, n)}")
+    sampler = ClockSampler(local_rank)
+    launches0 = _lib.lib().ndl_kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    sampler.start()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = _lib.lib().ndl_kernel_launches() - launches0
+    # end to end from pinned host memory on a 1 GiB prefix-sized buffer (same content law)
+    ne = min(n, 1 << 30)
+    host = data[n - ne:].cpu().pin_memory()
+    pat.find_long_ptrs(host.data_ptr(), ne, 1, 0, nb.MEM_HOST, stream.cuda_stream)
+    t0 = time.perf_counter()
+    e2e_steps = 3
+    for _ in range(e2e_steps):
+        r = pat.find_long_ptrs(host.data_ptr(), ne, 1, 0, nb.MEM_HOST, stream.cuda_stream)
+    e2e_s = time.perf_counter() - t0
+    assert r == (True, ne - 9, ne)
+    peak, peak_src = measured_peak_gbs()
+    value = n * args.steps / (ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[3]: 256-state DFA 'a[ab]{7}c', ONE haystack, find() start/end (int64), match in the last 9 bytes",
+                   "regex": regex, "mode": "find", "haystack_bytes": n, "l2": "haystack larger than L2"},
+        "matches_per_s": args.steps / (ms * 1e-3),
+        "e2e": {"value": ne * e2e_steps / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": ne, "d2h_bytes_per_step": 17, "steps": e2e_steps,
+                "note": f"host path measured on a {ne >> 20} MiB haystack"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": value, "peak": peak, "unit": "GB/s", "frac": value / peak, "traffic": None,
+                     "kernel": "long8_kernel (+ head/tail/seam helper kernels inside the timed call)", "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": n},
+    }
+    print(json.dumps(line), flush=True)
+
+
 def cpu_baseline(blob, data, offsets, cw):
     """The oracle port timed on this box's host cores on a bounded sample of the same workload."""
     from tests.oracle_lib import Oracle
@@ -302,13 +373,17 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c4long"])
     ap.add_argument("--lines", type=int, default=0, help="lines per GPU (default: the workload's full size)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
+    if args.workload == "c4long" and args.impl != "reference":
+        run_long(args, rank, local_rank, world)
+    elif args.impl == "reference":
+        if args.workload == "c4long":
+            args.workload = "c4b"
         run_reference(args, rank, world)
     else:
         run_ours(args, rank, local_rank, world)

@@ -15,6 +15,7 @@
 #include "host/pattern.h"
 #include "kernels/generic.cuh"
 #include "kernels/lines8.cuh"
+#include "kernels/long8.cuh"
 #include "needle_b200.h"
 
 namespace ndl {
@@ -299,9 +300,179 @@ int ndl_match_batch(ndl_pattern* p, int mode, const void* data, const uint64_t* 
 }
 
 int ndl_find_long(ndl_pattern* p, const void* data, uint64_t n_chars, int char_width, int64_t from, uint8_t* matched,
-                  int64_t* start, int64_t* end, int mem_kind, void* stream) {
-  (void)p; (void)data; (void)n_chars; (void)char_width; (void)from; (void)matched; (void)start; (void)end; (void)mem_kind; (void)stream;
-  return fail(NDL_EINVAL, "ndl_find_long: chunk-parallel single-haystack path is not built yet");
+                  int64_t* start, int64_t* end, int mem_kind, void* stream_) {
+  if (!p) return fail(NDL_EINVAL, "pattern must not be NULL");
+  if (char_width != 1 && char_width != 2) return fail(NDL_EINVAL, "char_width must be 1 or 2");
+  if (mem_kind != NDL_MEM_HOST && mem_kind != NDL_MEM_DEVICE) return fail(NDL_EINVAL, "mem_kind must be NDL_MEM_HOST or NDL_MEM_DEVICE");
+  if (!matched || !start || !end) return fail(NDL_EINVAL, "matched, start and end must not be NULL");
+  if (from < 0) return fail(NDL_EINVAL, "from must be >= 0");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NDL_CUDA(cudaSetDevice(p->device));
+  const int64_t n = static_cast<int64_t>(n_chars);
+  const int64_t kIntMax = INT64_MAX;
+
+  std::lock_guard<std::mutex> lock(p->ws_mutex);
+  // haystack on the device
+  const uint8_t* d_data = static_cast<const uint8_t*>(data);
+  if (mem_kind == NDL_MEM_HOST) {
+    int rc = ensure_workspace(p->ws, static_cast<size_t>(n_chars) * char_width + 64, 16, false, true);
+    if (rc != NDL_OK) return rc;
+    if (n_chars) NDL_CUDA(cudaMemcpyAsync(p->ws.data, data, static_cast<size_t>(n_chars) * char_width, cudaMemcpyHostToDevice, stream));
+    d_data = static_cast<const uint8_t*>(p->ws.data);
+  }
+  // scratch: SeqResult + 2 atomics + back result
+  struct Scratch { SeqResult r; unsigned long long first_seg, first_bad; int64_t back; };
+  Scratch* d_sc = nullptr;
+  NDL_CUDA(cudaMalloc(&d_sc, sizeof(Scratch)));
+  struct Guard { void* a; void* b; void* c; ~Guard() { cudaFree(a); cudaFree(b); cudaFree(c); } } guard{d_sc, nullptr, nullptr};
+  Scratch h;
+  const DevTable fwd = p->tables[kForwards].view();
+  const int dead = fwd.n_states;
+
+  // run one sequential walk and fetch its result
+  auto seq = [&](int64_t p0, int64_t p1, int32_t state0, int64_t count_from, int64_t last_init, SeqResult& out) -> int {
+    if (char_width == 1)
+      seq_walk_kernel<uint8_t><<<1, 32, 0, stream>>>(fwd, d_data, p0, p1, state0, count_from, last_init, &d_sc->r);
+    else
+      seq_walk_kernel<uint16_t><<<1, 32, 0, stream>>>(fwd, reinterpret_cast<const uint16_t*>(d_data), p0, p1, state0, count_from, last_init, &d_sc->r);
+    g_launches.fetch_add(1);
+    NDL_CUDA(cudaGetLastError());
+    NDL_CUDA(cudaMemcpyAsync(&out, &d_sc->r, sizeof(SeqResult), cudaMemcpyDeviceToHost, stream));
+    NDL_CUDA(cudaStreamSynchronize(stream));
+    return NDL_OK;
+  };
+
+  int64_t last = -1;
+  int rc = NDL_OK;
+  SeqResult r;
+  const bool root_acc = p->tables[kForwards].host.root_accepting;
+  const Lines8Blob& img = p->l8[NDL_MODE_FIND];
+  const bool fast = char_width == 1 && !root_acc && img.ok && from < n;
+
+  if (!fast) {
+    // plain sequential walk (accepting root, UTF-16, or no shared-memory image): DFAClassBuilder.java:335-471
+    last = root_acc ? (from < n ? from : 0) : -1;
+    if (from < n) {
+      if ((rc = seq(from, n, 0, from, last, r)) != NDL_OK) return rc;
+      last = r.last;
+    }
+  } else {
+    const uint32_t row_bytes = static_cast<uint32_t>(img.n_cols) * img.n_cols * 4u * img.replicated;
+    // head: exact walk up to the first 2 KB boundary
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(d_data) + static_cast<uintptr_t>(from);
+    int64_t head_end = from + static_cast<int64_t>(((a0 + 2047) & ~static_cast<uintptr_t>(2047)) - a0);
+    if (head_end > n) head_end = n;
+    if ((rc = seq(from, head_end, 0, from, -1, r)) != NDL_OK) return rc;
+    bool done = false;
+    if (r.state == dead) {
+      last = r.last;
+      done = true;
+    } else if (r.last != -1) {  // a match began in the head and may run on: follow it to its end
+      SeqResult r2;
+      if ((rc = seq(head_end, n, r.state, head_end, r.last, r2)) != NDL_OK) return rc;
+      last = r2.last;
+      done = true;
+    }
+    if (!done) {
+      const uint64_t n_tiles = static_cast<uint64_t>(n - head_end) / 2048;
+      int32_t state = r.state;
+      int64_t pos = head_end;
+      if (n_tiles > 0) {
+        uint32_t *d_guess = nullptr, *d_exit = nullptr;
+        NDL_CUDA(cudaMalloc(&d_guess, n_tiles * sizeof(uint32_t)));
+        guard.b = d_guess;
+        NDL_CUDA(cudaMalloc(&d_exit, n_tiles * sizeof(uint32_t)));
+        guard.c = d_exit;
+        NDL_CUDA(cudaMemsetAsync(&d_sc->first_seg, 0xff, 2 * sizeof(unsigned long long), stream));
+        Long8Params lp;
+        lp.data = d_data + head_end;
+        lp.n_tiles = n_tiles;
+        lp.image = img.dev;
+        lp.trans_bytes = img.trans_bytes;
+        lp.root_entry = img.root_entry;
+        lp.entry0 = static_cast<uint32_t>(r.state) * row_bytes;
+        lp.seam_guess = d_guess;
+        lp.seam_exit = d_exit;
+        lp.first_seg = &d_sc->first_seg;
+        lp.first_bad = &d_sc->first_bad;
+        NDL_CUDA(cudaFuncSetAttribute(long8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kL8DynSmem));
+        uint64_t want = (n_tiles + kL8Warps - 1) / kL8Warps;
+        int blocks = static_cast<int>(want < static_cast<uint64_t>(p->sm_count) ? want : p->sm_count);
+        long8_kernel<<<blocks, kL8Threads, kL8DynSmem, stream>>>(lp);
+        g_launches.fetch_add(1);
+        NDL_CUDA(cudaGetLastError());
+        long8_seam_kernel<<<p->sm_count * 4, 256, 0, stream>>>(d_guess, d_exit, n_tiles, &d_sc->first_bad);
+        g_launches.fetch_add(1);
+        NDL_CUDA(cudaGetLastError());
+        NDL_CUDA(cudaMemcpyAsync(&h, d_sc, sizeof(Scratch), cudaMemcpyDeviceToHost, stream));
+        NDL_CUDA(cudaStreamSynchronize(stream));
+        const unsigned long long kNone = ~0ull;
+        if (h.first_bad != kNone && (h.first_seg == kNone || h.first_bad <= h.first_seg)) {
+          // a guess was wrong before any match: the pattern remembers further back than the warm-up.
+          // Fall back to the exact sequential walk from the end of the head.
+          if ((rc = seq(head_end, n, r.state, head_end, -1, r)) != NDL_OK) return rc;
+          last = r.last;
+          done = true;
+        } else if (h.first_seg != kNone) {
+          // exact re-walk from the start of the first accepting segment
+          pos = head_end + static_cast<int64_t>(h.first_seg) * 64;
+          if (h.first_seg != 0) {
+            SeqResult w;
+            if ((rc = seq(pos - 16, pos, 0, pos, -1, w)) != NDL_OK) return rc;  // the verified guess
+            state = w.state;
+          }
+          if ((rc = seq(pos, n, state, pos, -1, r)) != NDL_OK) return rc;
+          last = r.last;
+          done = true;
+        } else {
+          // no match in the tiles: continue exactly from the (verified) exit of the last tile
+          uint32_t exit_off = 0;
+          NDL_CUDA(cudaMemcpyAsync(&exit_off, d_exit + (n_tiles - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+          NDL_CUDA(cudaStreamSynchronize(stream));
+          state = static_cast<int32_t>(exit_off / row_bytes);
+          pos = head_end + static_cast<int64_t>(n_tiles) * 2048;
+        }
+      }
+      if (!done) {
+        if ((rc = seq(pos, n, state, pos, -1, r)) != NDL_OK) return rc;
+        last = r.last;
+      }
+    }
+  }
+
+  // find(from, to) glue (DFAClassBuilder.java:625-659) with 64-bit indices
+  int64_t st = -1;
+  if (last != -1) {
+    if (p->cp.reverse_mode == kReverseFixedLength) {
+      st = last - p->cp.min_length;
+    } else {
+      BatchParams bp;
+      std::memset(&bp, 0, sizeof(bp));
+      bp.reverse_mode = p->cp.reverse_mode;
+      bp.reverse_char = p->cp.reverse_char;
+      bp.bwd = p->tables[kBackwards].view();
+      if (char_width == 1)
+        seq_back_kernel<uint8_t><<<1, 32, 0, stream>>>(bp, d_data, last - 1, from, kIntMax, &d_sc->back);
+      else
+        seq_back_kernel<uint16_t><<<1, 32, 0, stream>>>(bp, reinterpret_cast<const uint16_t*>(d_data), last - 1, from, kIntMax, &d_sc->back);
+      g_launches.fetch_add(1);
+      NDL_CUDA(cudaGetLastError());
+      NDL_CUDA(cudaMemcpyAsync(&st, &d_sc->back, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+      NDL_CUDA(cudaStreamSynchronize(stream));
+    }
+  }
+  const uint8_t m = last != -1;
+  if (mem_kind == NDL_MEM_HOST) {
+    *matched = m;
+    *start = st;
+    *end = last;
+  } else {
+    NDL_CUDA(cudaMemcpyAsync(matched, &m, 1, cudaMemcpyHostToDevice, stream));
+    NDL_CUDA(cudaMemcpyAsync(start, &st, sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+    NDL_CUDA(cudaMemcpyAsync(end, &last, sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+    NDL_CUDA(cudaStreamSynchronize(stream));
+  }
+  return NDL_OK;
 }
 
 }  // extern "C"

@@ -193,6 +193,34 @@ class Pattern:
         if rc != _lib.NDL_OK:
             _raise(rc, "ndl_match_batch")
 
+    def find_long(self, data: np.ndarray, from_: int = 0, char_width: int = 1):
+        """find() over ONE haystack of any length (64-bit offsets; BASELINE config 4) from a HOST array.
+        Returns (matched, start, end)."""
+        data = np.ascontiguousarray(data).view(np.uint8)
+        return self.find_long_ptrs(data.ctypes.data if data.size else 0, data.size // char_width, char_width, from_, _lib.MEM_HOST)
+
+    def find_long_ptrs(self, data_ptr: int, n_chars: int, char_width: int = 1, from_: int = 0, mem_kind: int = _lib.MEM_DEVICE,
+                       stream: int = 0):
+        """Raw-pointer form of find_long (device memory by default).  The three results come back on the host."""
+        m = ctypes.c_uint8()
+        st, en = ctypes.c_int64(), ctypes.c_int64()
+        if mem_kind == _lib.MEM_DEVICE:
+            # results are written through device pointers by the C ABI in that mode; use a small host round trip instead
+            import torch
+            out = torch.zeros(3, dtype=torch.int64, device=f"cuda:{self.device}")
+            mm = torch.zeros(1, dtype=torch.uint8, device=f"cuda:{self.device}")
+            rc = _lib.lib().ndl_find_long(self._h, data_ptr or None, n_chars, char_width, from_, mm.data_ptr(), out.data_ptr(),
+                                          out.data_ptr() + 8, mem_kind, stream or None)
+            if rc != _lib.NDL_OK:
+                _raise(rc, "ndl_find_long")
+            o = out.cpu().tolist()
+            return bool(mm.item()), int(o[0]), int(o[1])
+        rc = _lib.lib().ndl_find_long(self._h, data_ptr or None, n_chars, char_width, from_, ctypes.byref(m), ctypes.byref(st),
+                                      ctypes.byref(en), mem_kind, stream or None)
+        if rc != _lib.NDL_OK:
+            _raise(rc, "ndl_find_long")
+        return bool(m.value), st.value, en.value
+
     def find_all(self, strings: Sequence[Union[str, bytes]]):
         """Convenience: first find() per string.  Returns list of (matched, start, end)."""
         data, offsets, cw = pack_haystacks(strings)

@@ -1,0 +1,129 @@
+"""ndl_find_long: find() over one long haystack (BASELINE config 4), chunk-parallel on the GPU, against the
+oracle's sequential walk with 64-bit offsets.  Needs a CUDA device."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import needle_b200 as nb
+from tests import workloads
+from tests.oracle_lib import INT64_MAX, Oracle, lib as oracle_lib
+
+pytestmark = pytest.mark.gpu
+
+_P = {}
+
+
+def pair(regex, flags=0):
+    key = (regex, flags)
+    if key not in _P:
+        blob = nb.compile_to_bytes(regex, flags)
+        _P[key] = (nb.Pattern(blob, device=0), Oracle(blob))
+    return _P[key]
+
+
+def oracle_find_long(ora, data, from_=0, cw=1):
+    st, en = ctypes.c_int64(), ctypes.c_int64()
+    data = np.ascontiguousarray(data).view(np.uint8)
+    m = oracle_lib().ndlo_find(ora._h, data.ctypes.data, data.size // cw, cw, from_, INT64_MAX, ctypes.byref(st), ctypes.byref(en))
+    return bool(m), st.value, en.value
+
+
+def ab_buffer(n, seed):
+    rng = np.random.default_rng(seed)
+    return (rng.integers(0, 2, size=n, dtype=np.uint8) + ord("a")).astype(np.uint8)
+
+
+@pytest.mark.parametrize("n", [0, 1, 8, 9, 10, 100, 2047, 2048, 2049, 4096 + 9, 70_001, 3_000_000])
+def test_c4_match_at_the_very_end(n):
+    pat, ora = pair(workloads.REGEX["c4"])
+    data = ab_buffer(n, n)
+    if n >= 9:
+        data[n - 9] = ord("a")
+        data[n - 1] = ord("c")
+    got = pat.find_long(data)
+    assert got == oracle_find_long(ora, data)
+    if n >= 9:
+        assert got == (True, n - 9, n)
+
+
+def test_c4_match_positions_across_segment_and_tile_boundaries():
+    pat, ora = pair(workloads.REGEX["c4"])
+    n = 300_000
+    base = ab_buffer(n, 3)
+    for pos in [0, 1, 55, 56, 63, 64, 2040, 2047, 2048, 2050, 4090, 65_530, 131_072 - 4, 250_000, n - 9]:
+        data = base.copy()
+        data[pos] = ord("a")
+        data[pos + 8] = ord("c")
+        got = pat.find_long(data)
+        assert got == oracle_find_long(ora, data) == (True, pos, pos + 9), pos
+    # two matches: the leftmost wins; and find(from) skips the first
+    data = base.copy()
+    for pos in (10_000, 200_000):
+        data[pos] = ord("a")
+        data[pos + 8] = ord("c")
+    assert pat.find_long(data) == (True, 10_000, 10_009)
+    assert pat.find_long(data, from_=10_001) == oracle_find_long(ora, data, 10_001) == (True, 200_000, 200_009)
+    assert pat.find_long(data, from_=200_001) == (False, -1, -1)
+
+
+def test_unaligned_data_pointer_and_from():
+    pat, ora = pair(workloads.REGEX["c4"])
+    big = ab_buffer(500_000 + 37, 5)
+    for shift in (1, 7, 15, 37):
+        data = big[shift:]
+        data2 = data.copy()
+        data2[400_000] = ord("a")
+        data2[400_008] = ord("c")
+        for frm in (0, 3, 2048, 399_999):
+            assert pat.find_long(data2, from_=frm) == oracle_find_long(ora, data2, frm)
+
+
+@pytest.mark.parametrize("regex", [workloads.REGEX["c2"], workloads.REGEX["c3"], "Sherlock|Street", "[0-9]+x", "needle"])
+def test_other_patterns_on_text(regex):
+    pat, ora = pair(regex)
+    data, offsets = workloads.c3_lines(40_000)  # ~2.5 MB of text with planted e-mail addresses
+    data = data.copy()
+    data[2_000_000:2_000_011] = np.frombuffer(b"123-45-6789", dtype=np.uint8)
+    data[2_100_000:2_100_008] = np.frombuffer(b"Sherlock", dtype=np.uint8)
+    data[2_200_000:2_200_006] = np.frombuffer(b"needle", dtype=np.uint8)
+    for frm in (0, 1_000_000, 2_050_000, 2_150_000, 2_300_000):
+        assert pat.find_long(data, from_=frm) == oracle_find_long(ora, data, frm), (regex, frm)
+
+
+def test_long_memory_pattern_falls_back_to_the_exact_walk():
+    # `a.*c` (no newline in the data): the state after an 'a' persists, so the 16-byte guess is wrong and
+    # the call must notice and fall back.  Kept small: the fallback is a single-thread walk.
+    pat, ora = pair("q[a-z ]*7")
+    rng = np.random.default_rng(11)
+    alpha = np.frombuffer(b"abcdefghijklmnop rstuvwxyz", dtype=np.uint8)
+    data = alpha[rng.integers(0, len(alpha), size=200_000)].copy()
+    data[50_000] = ord("q")
+    data[150_000] = ord("7")
+    assert pat.find_long(data) == oracle_find_long(ora, data) == (True, 50_000, 150_001)
+
+
+def test_accepting_root_and_utf16():
+    pat, ora = pair("a*")
+    data = np.frombuffer(b"baaaa" * 1000, dtype=np.uint8)
+    assert pat.find_long(data) == oracle_find_long(ora, data) == (True, 0, 0)
+    assert pat.find_long(data, from_=1) == oracle_find_long(ora, data, 1)
+    pat, ora = pair(workloads.REGEX["c5"])
+    d16, _ = workloads.c5_lines(2000)
+    assert pat.find_long(d16, char_width=2) == oracle_find_long(ora, d16, 0, 2)
+
+
+def test_device_pointer_entry_and_gigabyte_scale():
+    """1 GiB of {a,b} generated on the device with the only match at the very end: the whole buffer must be
+    scanned, and the answer is known by construction (no 'c' anywhere else)."""
+    torch = pytest.importorskip("torch")
+    pat, _ = pair(workloads.REGEX["c4"])
+    n = 1 << 30
+    g = torch.Generator(device="cuda")
+    g.manual_seed(0x5EED0004)
+    data = torch.randint(ord("a"), ord("b") + 1, (n,), dtype=torch.uint8, device="cuda", generator=g)
+    tail = torch.tensor(list(b"abababbac"), dtype=torch.uint8, device="cuda")
+    data[n - 9:] = tail
+    assert pat.find_long_ptrs(data.data_ptr(), n) == (True, n - 9, n)
+    data[n - 1] = ord("b")
+    assert pat.find_long_ptrs(data.data_ptr(), n) == (False, -1, -1)
