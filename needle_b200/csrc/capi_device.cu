@@ -141,6 +141,9 @@ static int launch_batch(ndl_pattern* p, const BatchParams& bp, int char_width, u
     lp.image = img.dev;
     lp.trans_bytes = img.trans_bytes;
     lp.root_entry = img.root_entry;
+    lp.bwd_root = img.bwd_root;
+    lp.bwd_dead = img.bwd_dead;
+    lp.has_bwd = img.has_bwd ? 1 : 0;
     uint64_t max_tiles = (bp.n + 1023) / 1024;  // a CTA's 32 warps take 32 lines each per round
     int blocks = static_cast<int>(max_tiles < static_cast<uint64_t>(p->sm_count) ? max_tiles : p->sm_count);
     lines8_kernel<<<blocks, kL8Threads, kL8DynSmem, stream>>>(lp);
@@ -217,7 +220,10 @@ int ndl_pattern_create(const uint8_t* blob, size_t blob_len, int device, ndl_pat
   for (int mode = 0; mode < 3 && ae == cudaSuccess; mode++) {
     std::vector<uint8_t> img;
     Lines8Blob& b = p->l8[mode];
-    const bool ok = lines8_layout(p->tables[mode == NDL_MODE_FIND ? kForwards : mode].host, img, b);
+    const HostDeviceTable& fwd_t = p->tables[mode == NDL_MODE_FIND ? kForwards : mode].host;
+    const bool want_bwd = mode == NDL_MODE_FIND && p->cp.reverse_mode == kReverseTable;
+    bool ok = want_bwd && lines8_layout(fwd_t, &p->tables[kBackwards].host, img, b);
+    if (!ok) ok = lines8_layout(fwd_t, nullptr, img, b);  // reverse pass then walks the global tables
     if (!ok) continue;
     if (cudaMalloc(&b.dev, img.size()) != cudaSuccess ||
         cudaMemcpy(b.dev, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {

@@ -64,27 +64,36 @@ constexpr uint32_t kL8FlagMask = 0x3fffffffu;
 struct Lines8Blob {
   uint8_t* dev = nullptr;
   uint32_t trans_bytes = 0;  // multiple of 16
-  uint32_t root_entry = 0;   // E of "currently in the root state"
+  uint32_t root_entry = 0;   // E of "currently in the root state" (forward table)
+  uint32_t bwd_root = 0;     // same for the BACKWARDS table, when resident
+  uint32_t bwd_dead = 0;     // row offset of its DEAD row
   int replicated = 0;        // 32 or 1
   int n_cols = 0;            // C
+  bool has_bwd = false;
   bool ok = false;
 };
 
-// Build the shared-memory image of one device automaton for 2-char steps.  Returns false when the
-// pair table does not fit (the generic kernel handles the pattern then).
-inline bool lines8_layout(const HostDeviceTable& t, std::vector<uint8_t>& img, Lines8Blob& meta) {
-  const int rows = t.n_states + 1;
-  // compact the class columns to the ones byte values actually use
-  std::vector<int> col_of(t.n_classes, -1), class_of_col;
-  for (int b = 0; b < 256; b++) {
-    int k = t.cmap[b];
-    if (col_of[k] < 0) {
-      col_of[k] = static_cast<int>(class_of_col.size());
-      class_of_col.push_back(k);
+// Build the shared-memory image for 2-char steps: the forward automaton of the mode and, optionally, the
+// BACKWARDS automaton (find() of a variable-length pattern) behind it.  Both share one pair of class maps:
+// columns are the distinct (forward class, backward class) combinations the 256 byte values take.
+// Returns false when the pair tables do not fit (the generic kernel handles the pattern then).
+inline bool lines8_layout(const HostDeviceTable& f, const HostDeviceTable* b, std::vector<uint8_t>& img, Lines8Blob& meta) {
+  std::vector<std::pair<int, int>> col_classes;  // column -> (forward class, backward class)
+  int col_of_byte[256];
+  for (int v = 0; v < 256; v++) {
+    const std::pair<int, int> key{f.cmap[v], b ? b->cmap[v] : 0};
+    int c = -1;
+    for (size_t k = 0; k < col_classes.size(); k++)
+      if (col_classes[k] == key) c = static_cast<int>(k);
+    if (c < 0) {
+      c = static_cast<int>(col_classes.size());
+      col_classes.push_back(key);
     }
+    col_of_byte[v] = c;
   }
-  const int C = static_cast<int>(class_of_col.size());
-  const long pairs = static_cast<long>(rows) * C * C;
+  const int C = static_cast<int>(col_classes.size());
+  const int rows_f = f.n_states + 1, rows_b = b ? b->n_states + 1 : 0;
+  const long pairs = static_cast<long>(rows_f + rows_b) * C * C;
   int R;
   if (pairs * 128 <= static_cast<long>(kL8MaxTransBytes))
     R = 32;
@@ -94,28 +103,40 @@ inline bool lines8_layout(const HostDeviceTable& t, std::vector<uint8_t>& img, L
     return false;
   const uint32_t col_bytes = 4u * R;
   const uint32_t row_bytes = static_cast<uint32_t>(C) * C * col_bytes;
-  const uint32_t trans_bytes = (static_cast<uint32_t>(rows) * row_bytes + 15) & ~15u;
+  const uint32_t trans_bytes = (static_cast<uint32_t>(rows_f + rows_b) * row_bytes + 15) & ~15u;
   img.assign(kL8CmapBytes + trans_bytes, 0);
   auto put = [&](uint32_t off, uint32_t v) { std::memcpy(img.data() + off, &v, 4); };
-  for (int b = 0; b < 256; b++) {
-    const uint32_t c = static_cast<uint32_t>(col_of[t.cmap[b]]);
+  for (int v = 0; v < 256; v++) {
+    const uint32_t c = static_cast<uint32_t>(col_of_byte[v]);
     for (uint32_t lane = 0; lane < 32; lane++) {
-      put(b * 256 + lane * 4, c * C * col_bytes);                                              // CA
-      put(b * 256 + 128 + lane * 4, kL8AbsTrans + c * col_bytes + (R == 32 ? lane * 4 : 0));   // CB
+      put(v * 256 + lane * 4, c * C * col_bytes);                                              // CA
+      put(v * 256 + 128 + lane * 4, kL8AbsTrans + c * col_bytes + (R == 32 ? lane * 4 : 0));   // CB
     }
   }
-  for (int s = 0; s < rows; s++)
-    for (int c1 = 0; c1 < C; c1++) {
-      const int s1 = t.trans[static_cast<size_t>(s) * t.n_classes + class_of_col[c1]];
-      for (int c2 = 0; c2 < C; c2++) {
-        const int s2 = t.trans[static_cast<size_t>(s1) * t.n_classes + class_of_col[c2]];
-        const uint32_t e = static_cast<uint32_t>(s2) * row_bytes | (t.accept[s1] ? 0x80000000u : 0) | (t.accept[s2] ? 0x40000000u : 0);
-        for (int lane = 0; lane < R; lane++)
-          put(kL8CmapBytes + static_cast<uint32_t>(s) * row_bytes + (static_cast<uint32_t>(c1) * C + c2) * col_bytes + lane * 4, e);
+  auto emit = [&](const HostDeviceTable& t, int row0, bool backward) {
+    const int rows = t.n_states + 1;
+    for (int s = 0; s < rows; s++)
+      for (int c1 = 0; c1 < C; c1++) {
+        const int k1 = backward ? col_classes[c1].second : col_classes[c1].first;
+        const int s1 = t.trans[static_cast<size_t>(s) * t.n_classes + k1];
+        for (int c2 = 0; c2 < C; c2++) {
+          const int k2 = backward ? col_classes[c2].second : col_classes[c2].first;
+          const int s2 = t.trans[static_cast<size_t>(s1) * t.n_classes + k2];
+          const uint32_t e = static_cast<uint32_t>(row0 + s2) * row_bytes | (t.accept[s1] ? 0x80000000u : 0) | (t.accept[s2] ? 0x40000000u : 0);
+          for (int lane = 0; lane < R; lane++)
+            put(kL8CmapBytes + static_cast<uint32_t>(row0 + s) * row_bytes + (static_cast<uint32_t>(c1) * C + c2) * col_bytes + lane * 4, e);
+        }
       }
-    }
+  };
+  emit(f, 0, false);
+  meta.root_entry = 0;  // forward root = row 0
+  meta.has_bwd = b != nullptr;
+  if (b) {
+    emit(*b, rows_f, true);
+    meta.bwd_root = static_cast<uint32_t>(rows_f) * row_bytes;
+    meta.bwd_dead = static_cast<uint32_t>(rows_f + b->n_states) * row_bytes;
+  }
   meta.trans_bytes = trans_bytes;
-  meta.root_entry = 0;  // row 0 is the root
   meta.replicated = R;
   meta.n_cols = C;
   return true;
@@ -126,6 +147,8 @@ struct Lines8Params {
   const uint8_t* image;  // [cmap][trans]
   uint32_t trans_bytes;
   uint32_t root_entry;
+  uint32_t bwd_root, bwd_dead;
+  int has_bwd;  // BACKWARDS pair table resident: table-driven reverse pass runs on the staged tile
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -186,6 +209,52 @@ __device__ __forceinline__ void l8_pair(uint32_t word, uint32_t sel_a, uint32_t 
 __device__ __forceinline__ void l8_word(uint32_t w, uint32_t sel_a, uint32_t sel_b, uint32_t& e, uint32_t& mask) {
   l8_pair<0>(w, sel_a, sel_b, e, mask);
   l8_pair<2>(w, sel_a, sel_b, e, mask);
+}
+
+// The same step walking backwards: first char = byte K, second = byte K-1.
+template <int K>
+__device__ __forceinline__ void l8_pair_rev(uint32_t word, uint32_t sel_a, uint32_t sel_b, uint32_t& e, uint32_t& mask) {
+  const uint32_t ca = lds_tab(__byte_perm(word, sel_a, 0x7604u | (K << 4)));
+  const uint32_t cb = lds_tab(__byte_perm(word, sel_b, 0x7604u | ((K - 1) << 4)));
+  e = lds_tab((e & kL8FlagMask) + ca + cb);
+  mask = __funnelshift_l(e, mask, 2);
+}
+__device__ __forceinline__ void l8_word_rev(uint32_t w, uint32_t sel_a, uint32_t sel_b, uint32_t& e, uint32_t& mask) {
+  l8_pair_rev<3>(w, sel_a, sel_b, e, mask);
+  l8_pair_rev<1>(w, sel_a, sel_b, e, mask);
+}
+
+// indexBackwards(end - 1, 0) (DFAClassBuilder.java:529-586) over the staged tile.  `chunk_addr(c)` gives the
+// shared address of 16-byte chunk c of the byte space in which the line starts at `ps`; the match ends
+// (exclusive) at line index `last`.  Walks 16-byte windows downwards; steps that fall before the start of
+// the line only produce accept bits that are shifted out.  Returns the smallest accepting index, or INT_MAX.
+template <typename ChunkAddr>
+__device__ __forceinline__ int32_t l8_reverse(const Lines8Params& p, ChunkAddr chunk_addr, uint32_t ps, int32_t last, uint32_t sel_a,
+                                              uint32_t sel_b, bool bwd_root_accepting) {
+  int32_t st = bwd_root_accepting ? 0 : 0x7fffffff;
+  uint32_t e = p.bwd_root;
+  for (int32_t rem = last; rem > 0; rem -= 16) {
+    const uint32_t h = ps + static_cast<uint32_t>(rem);  // window = bytes [h - 16, h)
+    const uint32_t q = h >> 4, sh = h & 15u;
+    const uint4 y = lds_data16(chunk_addr(q));
+    const uint4 x = lds_data16(chunk_addr(q > 0 ? q - 1 : 0));
+    const bool q1 = (sh & 4u) != 0, q2 = (sh & 8u) != 0;
+    const uint32_t r8 = (sh & 3u) * 8u;
+    const uint32_t a0 = q2 ? x.z : x.x, a1 = q2 ? x.w : x.y, a2 = q2 ? y.x : x.z, a3 = q2 ? y.y : x.w;
+    const uint32_t a4 = q2 ? y.z : y.x, a5 = q2 ? y.w : y.y;
+    const uint32_t w0 = q1 ? a1 : a0, w1 = q1 ? a2 : a1, w2 = q1 ? a3 : a2, w3 = q1 ? a4 : a3, w4 = q1 ? a5 : a4;
+    uint32_t mask = 0;
+    l8_word_rev(__funnelshift_r(w3, w4, r8), sel_a, sel_b, e, mask);
+    l8_word_rev(__funnelshift_r(w2, w3, r8), sel_a, sel_b, e, mask);
+    l8_word_rev(__funnelshift_r(w1, w2, r8), sel_a, sel_b, e, mask);
+    l8_word_rev(__funnelshift_r(w0, w1, r8), sel_a, sel_b, e, mask);
+    const int32_t valid = rem < 16 ? rem : 16;
+    mask >>= (16 - valid);  // drop the steps taken before the start of the line
+    const int32_t cand = rem - valid + (__ffs(mask) - 1);
+    st = mask ? cand : st;
+    if ((e & kL8FlagMask) == p.bwd_dead) break;
+  }
+  return st;
 }
 
 // swizzled slot (in 16-byte units) of chunk `c` of tile-local line `line`; 2^log2cpl chunks per line.
@@ -317,7 +386,10 @@ __device__ __forceinline__ void l8_run(const Lines8Params& p, const uint32_t buf
           if (last != -1) {
             if (g.reverse_mode == 2)  // start = end - minLength (DFAClassBuilder.java:640-646)
               st = last - g.min_length;
-            else  // indexBackwards / single-char reverse scan (:529-614) over the global tables
+            else if (g.reverse_mode == 0 && p.has_bwd)  // indexBackwards (:529-586) on the staged tile
+              st = l8_reverse(p, [&](uint32_t ch) { return cur + (l8_slot(lane, ch & (G::kCpl - 1), LOG2CPL) << 4); }, 0u, last, sel_a,
+                              sel_b, g.bwd.root_accepting != 0);
+            else  // single-char reverse scan (:588-614), or no resident BACKWARDS table: global tables
               st = static_cast<int32_t>(dev_index_backwards<uint8_t>(g, data + g.offsets[i], last - 1, 0, 0x7fffffff));
           }
           g.matched[i] = last != -1;
@@ -455,6 +527,8 @@ __device__ __forceinline__ void l8_run_ragged(const Lines8Params& p, const uint3
         if (last != -1) {
           if (g.reverse_mode == 2)
             st = last - g.min_length;
+          else if (g.reverse_mode == 0 && p.has_bwd)
+            st = l8_reverse(p, [&](uint32_t ch) { return cur + l8_rslot(ch); }, pl.start, last, sel_a, sel_b, g.bwd.root_accepting != 0);
           else
             st = static_cast<int32_t>(dev_index_backwards<uint8_t>(g, data + g.offsets[i], last - 1, 0, 0x7fffffff));
         }
