@@ -39,6 +39,7 @@ WORKLOADS = {
     "c2": ("c2", "BASELINE configs[1]: '\\d{3}-\\d{2}-\\d{4}' find() over 10M synthetic 64-byte ASCII lines per GPU", workloads.c2_lines, 10_000_000, 1),
     "c4b": ("c4", "BASELINE configs[3] batched variant: 256-state DFA 'a[ab]{7}c' find() over 64-byte lines of {a,b}", workloads.c4_lines, 10_000_000, 1),
     "c3": ("c3", "BASELINE configs[2]: email-like regex find() over mixed-length lines (8..120 B)", workloads.c3_lines, 10_000_000, 1),
+    "c5": ("c5", "BASELINE configs[4]: BMP char-class regex find() over UTF-16LE lines of 32 chars (64 B)", workloads.c5_lines, 10_000_000, 2),
 }
 
 
@@ -170,6 +171,7 @@ def run_ours(args, rank, local_rank, world):
     # this rank's shard of the job: its own n lines (weak scaling), seeded by rank
     data_h, off_h = gen(n, seed=0x5EED0000 + 16 * rank + int(key[1]))
     in_bytes = int(off_h[-1] - off_h[0]) * cw
+    data_h = np.ascontiguousarray(data_h).view(np.uint8)
     pin = torch.cuda.is_available()
     data_p = torch.from_numpy(data_h).pin_memory() if pin else torch.from_numpy(data_h)
     off_p = torch.from_numpy(off_h.view(np.int64)).pin_memory()
@@ -265,8 +267,9 @@ def run_ours(args, rank, local_rank, world):
                     "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
             "gpu_launches": int(job_launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "lines8_kernel", "kernel_ms": kernel_ms, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": measured_traffic(args.workload) if n == default_lines else None,
+                         "kernel": "lines8_kernel" if cw == 1 else "generic_batch_kernel<uint16_t>", "kernel_ms": kernel_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": in_bytes,
                          "note": "algorithmic bytes = haystack bytes only (SURVEY.md 8d); the launch also reads 8 B/line of offsets and writes 9 B/line of results"},
         }
@@ -346,6 +349,16 @@ def run_long(args, rank, local_rank, world):
                      "algorithmic_bytes_per_launch": n},
     }
     print(json.dumps(line), flush=True)
+
+
+def measured_traffic(workload):
+    """DRAM bytes per launch of the bench kernel, from the committed ncu capture (None if not captured)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)[workload]
+        return t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        return None
 
 
 def cpu_baseline(blob, data, offsets, cw):

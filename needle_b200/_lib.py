@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libneedle_b200.so")
+LIB_PATH = os.environ.get("NEEDLE_B200_LIB", os.path.join(_HERE, "libneedle_b200.so"))
 
 NDL_OK = 0
 NDL_ESYNTAX, NDL_ECOMPILE, NDL_ETOOLARGE, NDL_EFLAGS = -1, -2, -3, -4

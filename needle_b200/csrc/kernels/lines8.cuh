@@ -329,7 +329,9 @@ __device__ __forceinline__ void l8_run(const Lines8Params& p, const uint32_t buf
     if (regular) {
       src += lane * 16;
 #pragma unroll
+#ifndef L8_EXPERIMENT_NO_STAGE
       for (uint32_t k = 0; k < G::kCopies; k++) cp_async16(buf + dst_off[k], src + 512 * k);
+#endif
     }
     cp_async_commit();
     return regular;
