@@ -67,7 +67,8 @@ struct ndl_pattern {
   int device = 0;
   int sm_count = 0;
   DeviceTableStorage tables[4];
-  Lines8Blob l8[3];  // per mode: shared-memory image of the byte-input kernel
+  Lines8Blob l8[3];   // per mode: shared-memory image of the lines8 kernel for byte haystacks
+  Lines8Blob l16[3];  // per mode: same for UTF-16 haystacks (when the class map has a supported char mode)
   std::mutex ws_mutex;
   Workspace ws;
 };
@@ -95,6 +96,7 @@ static void free_pattern(ndl_pattern* p) {
     cudaFree(t.accept);
   }
   for (auto& b : p->l8) cudaFree(b.dev);
+  for (auto& b : p->l16) cudaFree(b.dev);
   cudaFree(p->ws.data);
   cudaFree(p->ws.offsets);
   cudaFree(p->ws.from);
@@ -134,8 +136,8 @@ static int ensure_workspace(Workspace& ws, size_t data_bytes, uint64_t n, bool w
 static int launch_batch(ndl_pattern* p, const BatchParams& bp, int char_width, uint64_t total_chars, cudaStream_t stream) {
   if (bp.n == 0) return NDL_OK;
   (void)total_chars;
-  if (char_width == 1 && bp.from == nullptr && p->l8[bp.mode].ok && bp.n >= 2 && bp.n < (1ull << 31)) {
-    const Lines8Blob& img = p->l8[bp.mode];
+  const Lines8Blob& img = char_width == 1 ? p->l8[bp.mode] : p->l16[bp.mode];
+  if (bp.from == nullptr && img.ok && bp.n >= 2 && bp.n < (1ull << 31)) {
     Lines8Params lp;
     lp.g = bp;
     lp.image = img.dev;
@@ -143,6 +145,13 @@ static int launch_batch(ndl_pattern* p, const BatchParams& bp, int char_width, u
     lp.root_entry = img.root_entry;
     lp.bwd_root = img.bwd_root;
     lp.bwd_dead = img.bwd_dead;
+    lp.ua = img.ua;
+    lp.ub = img.ub;
+    lp.xa = img.xa;
+    lp.xb = img.xb;
+    lp.mixed_page = img.mixed_page;
+    lp.replicated = img.replicated;
+    lp.char_mode = img.char_mode;
     lp.has_bwd = img.has_bwd ? 1 : 0;
     uint64_t max_tiles = (bp.n + 1023) / 1024;  // a CTA's 32 warps take 32 lines each per round
     int blocks = static_cast<int>(max_tiles < static_cast<uint64_t>(p->sm_count) ? max_tiles : p->sm_count);
@@ -181,6 +190,15 @@ uint64_t ndl_kernel_launches(void) { return g_launches.load(); }
 
 int ndl_pattern_device(const ndl_pattern* p) { return p ? p->device : -1; }
 
+// Test hook (not in include/needle_b200.h): which kernel a (mode, char_width) batch without `from` offsets
+// takes.  -1: generic_batch_kernel; otherwise lines8 with char_mode | replicated << 8 | has_bwd << 16 | n_cols << 24.
+int ndl_debug_fast_path(const ndl_pattern* p, int mode, int char_width) {
+  if (!p || mode < 0 || mode > 2) return -1;
+  const Lines8Blob& b = char_width == 1 ? p->l8[mode] : p->l16[mode];
+  if (!b.ok) return -1;
+  return b.char_mode | (b.replicated << 8) | ((b.has_bwd ? 1 : 0) << 16) | (b.n_cols << 24);
+}
+
 int ndl_pattern_create(const uint8_t* blob, size_t blob_len, int device, ndl_pattern** out) {
   if (!out) return fail(NDL_EINVAL, "out must not be NULL");
   *out = nullptr;
@@ -217,22 +235,23 @@ int ndl_pattern_create(const uint8_t* blob, size_t blob_len, int device, ndl_pat
   }
   // shared-memory images of the byte-input kernel, one per mode
   cudaError_t ae = cudaFuncSetAttribute(lines8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kL8DynSmem);
-  for (int mode = 0; mode < 3 && ae == cudaSuccess; mode++) {
-    std::vector<uint8_t> img;
-    Lines8Blob& b = p->l8[mode];
-    const HostDeviceTable& fwd_t = p->tables[mode == NDL_MODE_FIND ? kForwards : mode].host;
-    const bool want_bwd = mode == NDL_MODE_FIND && p->cp.reverse_mode == kReverseTable;
-    bool ok = want_bwd && lines8_layout(fwd_t, &p->tables[kBackwards].host, img, b);
-    if (!ok) ok = lines8_layout(fwd_t, nullptr, img, b);  // reverse pass then walks the global tables
-    if (!ok) continue;
-    if (cudaMalloc(&b.dev, img.size()) != cudaSuccess ||
-        cudaMemcpy(b.dev, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
-      cudaGetLastError();
-      free_pattern(p);
-      return fail(NDL_ECUDA, "uploading the shared-memory table image failed");
+  for (int cw = 1; cw <= 2 && ae == cudaSuccess; cw++)
+    for (int mode = 0; mode < 3; mode++) {
+      const HostDeviceTable& fwd_t = p->tables[mode == NDL_MODE_FIND ? kForwards : mode].host;
+      const bool want_bwd = mode == NDL_MODE_FIND && p->cp.reverse_mode == kReverseTable;
+      std::vector<uint8_t> img;
+      Lines8Blob& b = cw == 1 ? p->l8[mode] : p->l16[mode];
+      bool ok = want_bwd && lines8_layout(fwd_t, &p->tables[kBackwards].host, cw, img, b);
+      if (!ok) ok = lines8_layout(fwd_t, nullptr, cw, img, b);  // reverse pass then walks the global tables
+      if (!ok) continue;
+      if (cudaMalloc(&b.dev, img.size()) != cudaSuccess ||
+          cudaMemcpy(b.dev, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError();
+        free_pattern(p);
+        return fail(NDL_ECUDA, "uploading the shared-memory table image failed");
+      }
+      b.ok = true;
     }
-    b.ok = true;
-  }
   if (ae != cudaSuccess) cudaGetLastError();  // device cannot give the kernel its shared memory: generic path only
   *out = p;
   return NDL_OK;

@@ -1,4 +1,5 @@
-// lines8: the tuned batch kernel for byte haystacks (char_width == 1), one haystack ("line") per lane.
+// lines8: the tuned batch kernel, one haystack ("line") per lane.  Byte haystacks (char_width == 1) and -
+// when the char -> class map allows it - UTF-16LE haystacks (char_width == 2, see "char modes" below).
 //
 // Per char the generated Java loop does two dependent array loads (BYTE_CLASSES[c], then
 // STATES[class + state*stride]) plus bookkeeping (DFAClassBuilder.java:438-465).  Here the automaton is
@@ -39,6 +40,8 @@
 
 #include <cstdint>
 #include <cstring>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "../device_image.h"
@@ -60,13 +63,27 @@ constexpr uint32_t kL8AbsEnd = kL8AbsBar + 16;
 constexpr uint32_t kL8DynSmem = kL8AbsEnd;  // covers the map for any dynamic base in [0, 0x400]
 constexpr uint32_t kL8FlagMask = 0x3fffffffu;
 
-// Device image for one mode: [cmap 64 KB][trans], plus what the kernel needs to start a walk.
+// Char modes.  The walk consumes 32-bit words of the haystack; what a "char" is depends on the mode:
+//   kCmBytes  char_width 1: four chars per word, class map indexed by the byte.
+//   kCmHi     char_width 2 and the class of a char depends only on its HIGH byte (e.g. `[؀-ۿ]+`):
+//             two chars per word, class map indexed by bytes 1 and 3 - the low bytes are never looked at.
+//   kCmMixed  char_width 2 and exactly one 256-char page is non-uniform while every other page has one
+//             common class (an ASCII pattern over UTF-16 text): class map indexed by the LOW byte, and a
+//             select replaces the looked-up value by the common class when the high byte is another page.
+// Any other UTF-16 class map is left to the generic kernel.
+enum { kCmBytes = 0, kCmHi = 1, kCmMixed = 2 };
+
+// Device image for one (mode, char width): [cmap 64 KB][trans], plus what the kernel needs to start a walk.
 struct Lines8Blob {
   uint8_t* dev = nullptr;
   uint32_t trans_bytes = 0;  // multiple of 16
   uint32_t root_entry = 0;   // E of "currently in the root state" (forward table)
   uint32_t bwd_root = 0;     // same for the BACKWARDS table, when resident
   uint32_t bwd_dead = 0;     // row offset of its DEAD row
+  uint32_t ua = 0, ub = 0;   // kCmMixed: CA / CB value of the class every other page has
+  uint32_t xa = 0, xb = 0;   // UTF-16 modes: CA / CB value of the class of U+FFFF
+  int mixed_page = 0;        // kCmMixed: the high byte of the non-uniform page
+  int char_mode = kCmBytes;
   int replicated = 0;        // 32 or 1
   int n_cols = 0;            // C
   bool has_bwd = false;
@@ -75,22 +92,54 @@ struct Lines8Blob {
 
 // Build the shared-memory image for 2-char steps: the forward automaton of the mode and, optionally, the
 // BACKWARDS automaton (find() of a variable-length pattern) behind it.  Both share one pair of class maps:
-// columns are the distinct (forward class, backward class) combinations the 256 byte values take.
-// Returns false when the pair tables do not fit (the generic kernel handles the pattern then).
-inline bool lines8_layout(const HostDeviceTable& f, const HostDeviceTable* b, std::vector<uint8_t>& img, Lines8Blob& meta) {
-  std::vector<std::pair<int, int>> col_classes;  // column -> (forward class, backward class)
-  int col_of_byte[256];
-  for (int v = 0; v < 256; v++) {
-    const std::pair<int, int> key{f.cmap[v], b ? b->cmap[v] : 0};
-    int c = -1;
-    for (size_t k = 0; k < col_classes.size(); k++)
-      if (col_classes[k] == key) c = static_cast<int>(k);
-    if (c < 0) {
-      c = static_cast<int>(col_classes.size());
-      col_classes.push_back(key);
+// columns are the distinct (forward class, backward class) combinations the class-map slots take.
+// Returns false when the class map has no supported char mode or the pair tables do not fit (the generic
+// kernel handles the pattern then).
+inline bool lines8_layout(const HostDeviceTable& f, const HostDeviceTable* b, int char_width, std::vector<uint8_t>& img,
+                          Lines8Blob& meta) {
+  using Key = std::pair<int, int>;
+  auto key_of = [&](int c) { return Key{f.cmap[c], b ? b->cmap[c] : 0}; };
+  Key slot_key[256];
+  Key uniform_key{0, 0};
+  int char_mode = kCmBytes, mixed_page = -1;
+  if (char_width == 1) {
+    for (int v = 0; v < 256; v++) slot_key[v] = key_of(v);
+  } else {
+    std::vector<int> mixed;
+    for (int hi = 0; hi < 256; hi++) {
+      // U+FFFF is always treated as an exception char (its class is 0 in every reference class map,
+      // DFA.java:451), so it does not make page 0xFF "mixed"
+      bool uniform = true;
+      for (int lo = 1; lo < 256 && uniform; lo++)
+        if ((hi << 8 | lo) != 0xFFFF) uniform = key_of(hi << 8 | lo) == key_of(hi << 8);
+      if (!uniform) mixed.push_back(hi);
     }
-    col_of_byte[v] = c;
+    if (mixed.empty()) {
+      char_mode = kCmHi;
+      for (int hi = 0; hi < 256; hi++) slot_key[hi] = key_of(hi << 8);
+    } else if (mixed.size() == 1) {
+      mixed_page = mixed[0];
+      const int other = mixed_page == 0 ? 1 : 0;
+      uniform_key = key_of(other << 8);
+      for (int hi = 0; hi < 256; hi++)
+        if (hi != mixed_page && !(key_of(hi << 8) == uniform_key)) return false;
+      char_mode = kCmMixed;
+      for (int lo = 0; lo < 256; lo++) slot_key[lo] = key_of(mixed_page << 8 | lo);
+    } else {
+      return false;
+    }
   }
+  std::vector<Key> col_classes;
+  auto col_for = [&](const Key& k) {
+    for (size_t i = 0; i < col_classes.size(); i++)
+      if (col_classes[i] == k) return static_cast<int>(i);
+    col_classes.push_back(k);
+    return static_cast<int>(col_classes.size() - 1);
+  };
+  int col_of_slot[256];
+  for (int v = 0; v < 256; v++) col_of_slot[v] = col_for(slot_key[v]);
+  const int col_uniform = char_mode == kCmMixed ? col_for(uniform_key) : 0;
+  const int col_exc = char_mode != kCmBytes ? col_for(key_of(0xFFFF)) : 0;
   const int C = static_cast<int>(col_classes.size());
   const int rows_f = f.n_states + 1, rows_b = b ? b->n_states + 1 : 0;
   const long pairs = static_cast<long>(rows_f + rows_b) * C * C;
@@ -107,7 +156,7 @@ inline bool lines8_layout(const HostDeviceTable& f, const HostDeviceTable* b, st
   img.assign(kL8CmapBytes + trans_bytes, 0);
   auto put = [&](uint32_t off, uint32_t v) { std::memcpy(img.data() + off, &v, 4); };
   for (int v = 0; v < 256; v++) {
-    const uint32_t c = static_cast<uint32_t>(col_of_byte[v]);
+    const uint32_t c = static_cast<uint32_t>(col_of_slot[v]);
     for (uint32_t lane = 0; lane < 32; lane++) {
       put(v * 256 + lane * 4, c * C * col_bytes);                                              // CA
       put(v * 256 + 128 + lane * 4, kL8AbsTrans + c * col_bytes + (R == 32 ? lane * 4 : 0));   // CB
@@ -139,6 +188,12 @@ inline bool lines8_layout(const HostDeviceTable& f, const HostDeviceTable* b, st
   meta.trans_bytes = trans_bytes;
   meta.replicated = R;
   meta.n_cols = C;
+  meta.char_mode = char_mode;
+  meta.mixed_page = mixed_page < 0 ? 0 : mixed_page;
+  meta.ua = static_cast<uint32_t>(col_uniform) * C * col_bytes;
+  meta.ub = kL8AbsTrans + static_cast<uint32_t>(col_uniform) * col_bytes;  // + lane*4 in the kernel when replicated
+  meta.xa = static_cast<uint32_t>(col_exc) * C * col_bytes;
+  meta.xb = kL8AbsTrans + static_cast<uint32_t>(col_exc) * col_bytes;
   return true;
 }
 
@@ -148,6 +203,11 @@ struct Lines8Params {
   uint32_t trans_bytes;
   uint32_t root_entry;
   uint32_t bwd_root, bwd_dead;
+  uint32_t ua, ub;       // kCmMixed
+  uint32_t xa, xb;       // UTF-16 modes: U+FFFF
+  int mixed_page;
+  int replicated;
+  int char_mode;
   int has_bwd;  // BACKWARDS pair table resident: table-driven reverse pass runs on the staged tile
 };
 
@@ -197,59 +257,102 @@ __device__ __forceinline__ uint4 lds_data16(uint32_t addr) {
   return v;
 }
 
-// One 2-char step on bytes K, K+1 of `word`.  sel_a = 0x00010000 | lane*4, sel_b = sel_a | 0x80.
-template <int K>
-__device__ __forceinline__ void l8_pair(uint32_t word, uint32_t sel_a, uint32_t sel_b, uint32_t& e, uint32_t& mask) {
-  // bytes: [0] <- sel.b0 (lane*4 [+128]), [1] <- word.bK, [2] <- sel.b2 (0x01), [3] <- sel.b3 (0x00)
-  const uint32_t ca = lds_tab(__byte_perm(word, sel_a, 0x7604u | (K << 4)));
-  const uint32_t cb = lds_tab(__byte_perm(word, sel_b, 0x7604u | ((K + 1) << 4)));
+// Per-lane constants of the walk.  sel_a = 0x00010000 | lane*4 selects the CA half of a class-map slot,
+// sel_b = sel_a | 0x80 the CB half: bytes {lane*4 [+128], <haystack byte>, 0x01, 0x00} of the address.
+struct L8Ctx {
+  uint32_t sel_a, sel_b;
+  uint32_t page1, page3;  // kCmMixed: mixed page number positioned at byte 1 / byte 3 of a word
+  uint32_t ua, ub;        // kCmMixed: CA / CB value of the common class of all other pages
+  uint32_t xa, xb;        // UTF-16 modes: CA / CB value of U+FFFF, whose class never follows its page
+};
+
+// One 2-char step.  KA / KB: byte index (within the 32-bit word) that selects the class-map slot of the
+// first / second char; HA / HB (kCmMixed only): byte index holding that char's high byte.
+template <int CM, int KA, int KB, int HA, int HB>
+__device__ __forceinline__ void l8_step2(uint32_t word, const L8Ctx& cx, uint32_t& e, uint32_t& mask) {
+  uint32_t ca = lds_tab(__byte_perm(word, cx.sel_a, 0x7604u | (KA << 4)));
+  uint32_t cb = lds_tab(__byte_perm(word, cx.sel_b, 0x7604u | (KB << 4)));
+  if (CM == kCmMixed) {
+    ca = ((word & (0xffu << (8 * HA))) == (HA == 1 ? cx.page1 : cx.page3)) ? ca : cx.ua;
+    cb = ((word & (0xffu << (8 * HB))) == (HB == 1 ? cx.page1 : cx.page3)) ? cb : cx.ub;
+  }
+  if (CM != kCmBytes) {  // the char in the low (H == 1) / high (H == 3) half of the word is U+FFFF
+    ca = (HA == 1 ? (word & 0xffffu) == 0xffffu : word >= 0xffff0000u) ? cx.xa : ca;
+    cb = (HB == 1 ? (word & 0xffffu) == 0xffffu : word >= 0xffff0000u) ? cx.xb : cb;
+  }
   e = lds_tab((e & kL8FlagMask) + ca + cb);
   mask = __funnelshift_l(e, mask, 2);  // mask = mask << 2 | accept(1st) << 1 | accept(2nd)
 }
-__device__ __forceinline__ void l8_word(uint32_t w, uint32_t sel_a, uint32_t sel_b, uint32_t& e, uint32_t& mask) {
-  l8_pair<0>(w, sel_a, sel_b, e, mask);
-  l8_pair<2>(w, sel_a, sel_b, e, mask);
-}
 
-// The same step walking backwards: first char = byte K, second = byte K-1.
-template <int K>
-__device__ __forceinline__ void l8_pair_rev(uint32_t word, uint32_t sel_a, uint32_t sel_b, uint32_t& e, uint32_t& mask) {
-  const uint32_t ca = lds_tab(__byte_perm(word, sel_a, 0x7604u | (K << 4)));
-  const uint32_t cb = lds_tab(__byte_perm(word, sel_b, 0x7604u | ((K - 1) << 4)));
-  e = lds_tab((e & kL8FlagMask) + ca + cb);
-  mask = __funnelshift_l(e, mask, 2);
+// All chars of one word, forwards / backwards.
+template <int CM>
+__device__ __forceinline__ void l8_word(uint32_t w, const L8Ctx& cx, uint32_t& e, uint32_t& mask) {
+  if (CM == kCmBytes) {
+    l8_step2<CM, 0, 1, 0, 0>(w, cx, e, mask);
+    l8_step2<CM, 2, 3, 0, 0>(w, cx, e, mask);
+  } else if (CM == kCmHi) {
+    l8_step2<CM, 1, 3, 1, 3>(w, cx, e, mask);
+  } else {
+    l8_step2<CM, 0, 2, 1, 3>(w, cx, e, mask);
+  }
 }
-__device__ __forceinline__ void l8_word_rev(uint32_t w, uint32_t sel_a, uint32_t sel_b, uint32_t& e, uint32_t& mask) {
-  l8_pair_rev<3>(w, sel_a, sel_b, e, mask);
-  l8_pair_rev<1>(w, sel_a, sel_b, e, mask);
+template <int CM>
+__device__ __forceinline__ void l8_word_rev(uint32_t w, const L8Ctx& cx, uint32_t& e, uint32_t& mask) {
+  if (CM == kCmBytes) {
+    l8_step2<CM, 3, 2, 0, 0>(w, cx, e, mask);
+    l8_step2<CM, 1, 0, 0, 0>(w, cx, e, mask);
+  } else if (CM == kCmHi) {
+    l8_step2<CM, 3, 1, 3, 1>(w, cx, e, mask);
+  } else {
+    l8_step2<CM, 2, 0, 3, 1>(w, cx, e, mask);
+  }
 }
+template <int CM>
+struct L8Chars {
+  static constexpr int kBytes = CM == kCmBytes ? 1 : 2;   // bytes per char
+  static constexpr int kPerChunk = 16 / kBytes;           // chars (= accept bits) per 16-byte chunk
+};
 
-// indexBackwards(end - 1, 0) (DFAClassBuilder.java:529-586) over the staged tile.  `chunk_addr(c)` gives the
-// shared address of 16-byte chunk c of the byte space in which the line starts at `ps`; the match ends
-// (exclusive) at line index `last`.  Walks 16-byte windows downwards; steps that fall before the start of
-// the line only produce accept bits that are shifted out.  Returns the smallest accepting index, or INT_MAX.
-template <typename ChunkAddr>
-__device__ __forceinline__ int32_t l8_reverse(const Lines8Params& p, ChunkAddr chunk_addr, uint32_t ps, int32_t last, uint32_t sel_a,
-                                              uint32_t sel_b, bool bwd_root_accepting) {
-  int32_t st = bwd_root_accepting ? 0 : 0x7fffffff;
-  uint32_t e = p.bwd_root;
-  for (int32_t rem = last; rem > 0; rem -= 16) {
-    const uint32_t h = ps + static_cast<uint32_t>(rem);  // window = bytes [h - 16, h)
-    const uint32_t q = h >> 4, sh = h & 15u;
-    const uint4 y = lds_data16(chunk_addr(q));
-    const uint4 x = lds_data16(chunk_addr(q > 0 ? q - 1 : 0));
-    const bool q1 = (sh & 4u) != 0, q2 = (sh & 8u) != 0;
-    const uint32_t r8 = (sh & 3u) * 8u;
+// Realign 16 bytes that start `sh` bytes into chunk x (continuing in chunk y) into four words.
+struct L8Align {
+  bool q1, q2;
+  uint32_t r8;
+  __device__ __forceinline__ explicit L8Align(uint32_t sh) : q1((sh & 4u) != 0), q2((sh & 8u) != 0), r8((sh & 3u) * 8u) {}
+  __device__ __forceinline__ void apply(const uint4& x, const uint4& y, uint32_t (&w)[4]) const {
     const uint32_t a0 = q2 ? x.z : x.x, a1 = q2 ? x.w : x.y, a2 = q2 ? y.x : x.z, a3 = q2 ? y.y : x.w;
     const uint32_t a4 = q2 ? y.z : y.x, a5 = q2 ? y.w : y.y;
     const uint32_t w0 = q1 ? a1 : a0, w1 = q1 ? a2 : a1, w2 = q1 ? a3 : a2, w3 = q1 ? a4 : a3, w4 = q1 ? a5 : a4;
+    w[0] = __funnelshift_r(w0, w1, r8);
+    w[1] = __funnelshift_r(w1, w2, r8);
+    w[2] = __funnelshift_r(w2, w3, r8);
+    w[3] = __funnelshift_r(w3, w4, r8);
+  }
+};
+
+// indexBackwards(end - 1, 0) (DFAClassBuilder.java:529-586) over the staged tile.  `chunk_addr(c)` gives the
+// shared address of 16-byte chunk c of the byte space in which the line starts at byte `ps`; the match ends
+// (exclusive) at char index `last`.  Walks 16-byte windows downwards; steps that fall before the start of
+// the line only produce accept bits that are shifted out.  Returns the smallest accepting index, or INT_MAX.
+template <int CM, typename ChunkAddr>
+__device__ __forceinline__ int32_t l8_reverse(const Lines8Params& p, ChunkAddr chunk_addr, uint32_t ps, int32_t last, const L8Ctx& cx,
+                                              bool bwd_root_accepting) {
+  constexpr int kPer = L8Chars<CM>::kPerChunk;
+  int32_t st = bwd_root_accepting ? 0 : 0x7fffffff;
+  uint32_t e = p.bwd_root;
+  for (int32_t rem = last; rem > 0; rem -= kPer) {
+    const uint32_t h = ps + static_cast<uint32_t>(rem) * L8Chars<CM>::kBytes;  // window = bytes [h - 16, h)
+    const uint32_t q = h >> 4;
+    const uint4 y = lds_data16(chunk_addr(q));
+    const uint4 x = lds_data16(chunk_addr(q > 0 ? q - 1 : 0));
+    uint32_t w[4];
+    L8Align(h & 15u).apply(x, y, w);
     uint32_t mask = 0;
-    l8_word_rev(__funnelshift_r(w3, w4, r8), sel_a, sel_b, e, mask);
-    l8_word_rev(__funnelshift_r(w2, w3, r8), sel_a, sel_b, e, mask);
-    l8_word_rev(__funnelshift_r(w1, w2, r8), sel_a, sel_b, e, mask);
-    l8_word_rev(__funnelshift_r(w0, w1, r8), sel_a, sel_b, e, mask);
-    const int32_t valid = rem < 16 ? rem : 16;
-    mask >>= (16 - valid);  // drop the steps taken before the start of the line
+    l8_word_rev<CM>(w[3], cx, e, mask);
+    l8_word_rev<CM>(w[2], cx, e, mask);
+    l8_word_rev<CM>(w[1], cx, e, mask);
+    l8_word_rev<CM>(w[0], cx, e, mask);
+    const int32_t valid = rem < kPer ? rem : kPer;
+    mask >>= (kPer - valid);  // drop the steps taken before the start of the line
     const int32_t cand = rem - valid + (__ffs(mask) - 1);
     st = mask ? cand : st;
     if ((e & kL8FlagMask) == p.bwd_dead) break;
@@ -266,25 +369,58 @@ __device__ __forceinline__ uint32_t l8_slot(uint32_t line, uint32_t c, int log2c
 }
 
 // Generic per-thread walk of line i straight from global memory (irregular tiles).
+template <typename CharT>
 __device__ __forceinline__ void l8_slow_line(const BatchParams& g, uint64_t i) {
   const uint64_t o0 = g.offsets[i], o1 = g.offsets[i + 1];
-  const uint8_t* s = static_cast<const uint8_t*>(g.data) + o0;
+  const CharT* s = static_cast<const CharT*>(g.data) + o0;
   const int64_t len = static_cast<int64_t>(o1 - o0);
   if (g.mode == 0) {
-    g.matched[i] = dev_matches<uint8_t>(g, s, len);
+    g.matched[i] = dev_matches<CharT>(g, s, len);
   } else if (g.mode == 1) {
-    g.matched[i] = dev_contained_in<uint8_t>(g, s, len);
+    g.matched[i] = dev_contained_in<CharT>(g, s, len);
   } else {
-    const int64_t e = dev_index_forwards<uint8_t>(g, s, len, 0);
+    const int64_t e = dev_index_forwards<CharT>(g, s, len, 0);
     int64_t st = -1;
-    if (e != -1) st = (g.reverse_mode == 2) ? e - g.min_length : dev_index_backwards<uint8_t>(g, s, e - 1, 0, 0x7fffffff);
+    if (e != -1) st = (g.reverse_mode == 2) ? e - g.min_length : dev_index_backwards<CharT>(g, s, e - 1, 0, 0x7fffffff);
     g.matched[i] = e != -1;
     g.start[i] = static_cast<int32_t>(st);
     g.end[i] = static_cast<int32_t>(e);
   }
 }
 
-// The walk of one regular warp tile, specialised on the line length (L = 16 << LOG2CPL bytes).
+// Results of one line.  `last`: char index after the last accepting step or -1; `tail_accept`: the state at
+// the end of the line is accepting (matches()); ps / chunk_addr: where the line sits in shared memory.
+template <int CM, typename CharT, typename ChunkAddr>
+__device__ __forceinline__ void l8_finish(const Lines8Params& p, const L8Ctx& cx, uint64_t i, uint32_t len_chars, int32_t last,
+                                          bool tail_accept, uint32_t ps, ChunkAddr chunk_addr) {
+  const BatchParams& g = p.g;
+  if (g.mode == 0) {
+    bool m = tail_accept;
+    if (g.min_length > 4 && static_cast<uint32_t>(g.min_length) > len_chars) m = false;  // DFAMethodComponents.java:75-93
+    if (g.max_length != -1 && len_chars > static_cast<uint32_t>(g.max_length)) m = false;
+    g.matched[i] = m;
+  } else if (g.mode == 1) {
+    g.matched[i] = last != -1;  // accepting rows of the containedIn automaton are absorbing
+  } else {
+    int32_t st = -1;
+    if (last != -1) {
+      if (g.reverse_mode == 2)  // start = end - minLength (DFAClassBuilder.java:640-646)
+        st = last - g.min_length;
+      else if (g.reverse_mode == 0 && p.has_bwd)  // indexBackwards (:529-586) on the staged tile
+        st = l8_reverse<CM>(p, chunk_addr, ps, last, cx, g.bwd.root_accepting != 0);
+      else  // single-char reverse scan (:588-614), or no resident BACKWARDS table: global tables
+        st = static_cast<int32_t>(dev_index_backwards<CharT>(g, static_cast<const CharT*>(g.data) + g.offsets[i], last - 1, 0, 0x7fffffff));
+    }
+    g.matched[i] = last != -1;
+    g.start[i] = st;
+    g.end[i] = last;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fixed-length lines: the walk of regular warp tiles, specialised on the line length in BYTES
+// (16 << LOG2CPL) and the char mode.
+// ---------------------------------------------------------------------------------------------
 template <int LOG2CPL>
 struct L8Geom {
   static constexpr uint32_t kCpl = 1u << LOG2CPL;                                 // 16-byte chunks per line
@@ -293,28 +429,30 @@ struct L8Geom {
   static constexpr uint32_t kCopies = kTileLines * kCpl / 32u;                    // cp.async per lane per tile
 };
 
-template <int LOG2CPL>
-__device__ __forceinline__ void l8_run(const Lines8Params& p, const uint32_t buf0, const uint32_t buf1, const uint32_t lane,
-                                       const uint32_t warp_global, const uint32_t n_warps) {
+template <int LOG2CPL, int CM>
+__device__ __forceinline__ void l8_run(const Lines8Params& p, const L8Ctx& cx, const uint32_t buf0, const uint32_t buf1,
+                                       const uint32_t lane, const uint32_t warp_global, const uint32_t n_warps) {
   using G = L8Geom<LOG2CPL>;
+  using CharT = typename std::conditional<CM == kCmBytes, uint8_t, uint16_t>::type;
+  constexpr uint32_t kCharBytes = L8Chars<CM>::kBytes;
+  constexpr uint32_t kPer = L8Chars<CM>::kPerChunk;
+  constexpr uint32_t kLenChars = G::kL / kCharBytes;
   const BatchParams& g = p.g;
   const uint8_t* const data = static_cast<const uint8_t*>(g.data);
   const uint32_t n = static_cast<uint32_t>(g.n);  // the host only takes this path for n < 2^31
   const uint32_t n_full = n / G::kTileLines;
   const bool active = lane < G::kTileLines;
 
-  // per-lane constants: where this lane's copies land, and where its own line's chunks are read from
+  // per-lane constants: where this lane's copies land
   uint32_t dst_off[G::kCopies];
 #pragma unroll
   for (uint32_t k = 0; k < G::kCopies; k++) {
     const uint32_t c = lane + 32 * k;
     dst_off[k] = l8_slot(c >> LOG2CPL, c & (G::kCpl - 1), LOG2CPL) << 4;
   }
-  const uint32_t sel_a = 0x00010000u | (lane * 4);
-  const uint32_t sel_b = sel_a | 0x80u;
   const uint32_t lane_line = active ? lane : 0;
 
-  // offsets of line (tile * kTileLines + lane) and the next one
+  // offsets (in chars) of line (tile * kTileLines + lane) and the next one
   auto load_offsets = [&](uint32_t tile, uint64_t& o0, uint64_t& o1) {
     const uint32_t i = tile * G::kTileLines + lane_line;
     o0 = g.offsets[i];
@@ -322,16 +460,14 @@ __device__ __forceinline__ void l8_run(const Lines8Params& p, const uint32_t buf
   };
   // Issue the copies of a tile whose offsets are (o0, o1); returns whether the tile is regular.
   auto stage = [&](uint64_t o0, uint64_t o1, uint32_t buf) -> bool {
-    const uint64_t tile_off = o0 - static_cast<uint64_t>(lane_line) * G::kL;  // same on every lane iff regular
+    const uint64_t tile_off = o0 * kCharBytes - static_cast<uint64_t>(lane_line) * G::kL;  // bytes; same on every lane iff regular
     const uint8_t* src = data + tile_off;
-    const bool ok = (o1 - o0 == G::kL) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    const bool ok = (o1 - o0 == kLenChars) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
     const bool regular = __all_sync(0xffffffffu, ok) != 0;
     if (regular) {
       src += lane * 16;
 #pragma unroll
-#ifndef L8_EXPERIMENT_NO_STAGE
       for (uint32_t k = 0; k < G::kCopies; k++) cp_async16(buf + dst_off[k], src + 512 * k);
-#endif
     }
     cp_async_commit();
     return regular;
@@ -366,41 +502,22 @@ __device__ __forceinline__ void l8_run(const Lines8Params& p, const uint32_t buf
 #pragma unroll
         for (uint32_t c = 0; c < G::kCpl; c++) {
           const uint4 w = lds_data16(cur + (l8_slot(lane, c, LOG2CPL) << 4));
-          l8_word(w.x, sel_a, sel_b, e, mask);
-          l8_word(w.y, sel_a, sel_b, e, mask);
-          l8_word(w.z, sel_a, sel_b, e, mask);
-          l8_word(w.w, sel_a, sel_b, e, mask);
-          if ((c & 1) || c + 1 == G::kCpl) {  // mask holds <= 32 chars; bit 0 = the most recent one
-            const int32_t cand = static_cast<int32_t>((c + 1) * 16 + 1) - __ffs(mask);
+          l8_word<CM>(w.x, cx, e, mask);
+          l8_word<CM>(w.y, cx, e, mask);
+          l8_word<CM>(w.z, cx, e, mask);
+          l8_word<CM>(w.w, cx, e, mask);
+          constexpr uint32_t kFlush = 32 / kPer;  // chunks whose accept bits fit in the 32-bit mask
+          if ((c % kFlush) == kFlush - 1 || c + 1 == G::kCpl) {  // bit 0 = the most recent char
+            const int32_t cand = static_cast<int32_t>((c + 1) * kPer + 1) - __ffs(mask);
             last = mask ? cand : last;
             mask = 0;
           }
         }
-        if (g.mode == 0) {
-          bool m = (e & 0x40000000u) != 0;
-          if (g.min_length > 4 && static_cast<uint32_t>(g.min_length) > G::kL) m = false;  // DFAMethodComponents.java:75-93
-          if (g.max_length != -1 && G::kL > static_cast<uint32_t>(g.max_length)) m = false;
-          g.matched[i] = m;
-        } else if (g.mode == 1) {
-          g.matched[i] = (e & 0x40000000u) != 0;
-        } else {
-          int32_t st = -1;
-          if (last != -1) {
-            if (g.reverse_mode == 2)  // start = end - minLength (DFAClassBuilder.java:640-646)
-              st = last - g.min_length;
-            else if (g.reverse_mode == 0 && p.has_bwd)  // indexBackwards (:529-586) on the staged tile
-              st = l8_reverse(p, [&](uint32_t ch) { return cur + (l8_slot(lane, ch & (G::kCpl - 1), LOG2CPL) << 4); }, 0u, last, sel_a,
-                              sel_b, g.bwd.root_accepting != 0);
-            else  // single-char reverse scan (:588-614), or no resident BACKWARDS table: global tables
-              st = static_cast<int32_t>(dev_index_backwards<uint8_t>(g, data + g.offsets[i], last - 1, 0, 0x7fffffff));
-          }
-          g.matched[i] = last != -1;
-          g.start[i] = st;
-          g.end[i] = last;
-        }
+        l8_finish<CM, CharT>(p, cx, i, kLenChars, last, (e & 0x40000000u) != 0, 0u,
+                             [&](uint32_t ch) { return cur + (l8_slot(lane, ch & (G::kCpl - 1), LOG2CPL) << 4); });
       }
     } else if (active) {
-      l8_slow_line(g, i);
+      l8_slow_line<CharT>(g, i);
     }
     __syncwarp();  // every lane is done with `cur` before the stage after next overwrites it
     regular = regular_next;
@@ -412,7 +529,7 @@ __device__ __forceinline__ void l8_run(const Lines8Params& p, const uint32_t buf
   // the partial last tile
   if (warp_global == 0) {
     const uint32_t i = n_full * G::kTileLines + lane;
-    if (i < n) l8_slow_line(g, i);
+    if (i < n) l8_slow_line<CharT>(g, i);
   }
 }
 
@@ -426,30 +543,32 @@ __device__ __forceinline__ void l8_run(const Lines8Params& p, const uint32_t buf
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t l8_rslot(uint32_t c) { return (c ^ ((c >> 3) & 7)) << 4; }
 
-__device__ __forceinline__ void l8_run_ragged(const Lines8Params& p, const uint32_t buf0, const uint32_t buf1, const uint32_t lane,
-                                              const uint32_t warp_global, const uint32_t n_warps) {
+template <int CM>
+__device__ __forceinline__ void l8_run_ragged(const Lines8Params& p, const L8Ctx& cx, const uint32_t buf0, const uint32_t buf1,
+                                              const uint32_t lane, const uint32_t warp_global, const uint32_t n_warps) {
+  using CharT = typename std::conditional<CM == kCmBytes, uint8_t, uint16_t>::type;
+  constexpr uint32_t kCharBytes = L8Chars<CM>::kBytes;
+  constexpr uint32_t kPer = L8Chars<CM>::kPerChunk;
   const BatchParams& g = p.g;
   const uint8_t* const data = static_cast<const uint8_t*>(g.data);
   const uint32_t n = static_cast<uint32_t>(g.n);
   const uint32_t per_warp = (n + n_warps - 1) / n_warps;
   const uint32_t lo = min(n, warp_global * per_warp), hi = min(n, lo + per_warp);
-  const uint32_t sel_a = 0x00010000u | (lane * 4);
-  const uint32_t sel_b = sel_a | 0x80u;
   constexpr uint32_t kCap = kL8WarpBuf - 16;  // the last 16 bytes stay free for the window that runs past the tile
 
   struct Plan {
     uint32_t count;   // lines in the tile (0: the first line alone does not fit)
     uint32_t start;   // this lane's line: first byte, relative to the tile buffer
-    uint32_t len;     // this lane's line length
+    uint32_t len;     // this lane's line length in chars
   };
   // Plan the tile that starts at line c and issue its copies into buf.
   auto plan_and_stage = [&](uint32_t c, uint32_t buf) -> Plan {
     Plan pl;
     pl.count = 0; pl.start = 0; pl.len = 0;
     if (c < hi) {
-      const uint64_t s0 = g.offsets[c];
+      const uint64_t s0 = g.offsets[c] * kCharBytes;  // bytes
       const uint32_t idx = min(c + lane + 1, hi);
-      const uint64_t e = g.offsets[idx];
+      const uint64_t e = g.offsets[idx] * kCharBytes;
       const uint32_t slack = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(data) + s0) & 15u;
       const uint64_t rel_end = e - s0 + slack;  // end of this lane's line relative to the tile buffer
       const bool fits = (c + lane < hi) && rel_end <= kCap;
@@ -459,7 +578,7 @@ __device__ __forceinline__ void l8_run_ragged(const Lines8Params& p, const uint3
       uint32_t prev = __shfl_up_sync(0xffffffffu, end32, 1);
       if (lane == 0) prev = slack;
       pl.start = prev;
-      pl.len = end32 - prev;
+      pl.len = (end32 - prev) / kCharBytes;
       if (pl.count) {
         const uint32_t total = __shfl_sync(0xffffffffu, end32, pl.count - 1);
         const uint32_t n_chunks = (total + 15) >> 4;
@@ -477,7 +596,7 @@ __device__ __forceinline__ void l8_run_ragged(const Lines8Params& p, const uint3
   while (c < hi) {
     if (pl.count == 0) {  // a line longer than the buffer: walk it straight from global memory
       cp_async_wait<0>();
-      if (lane == 0) l8_slow_line(g, c);
+      if (lane == 0) l8_slow_line<CharT>(g, c);
       c += 1;
       __syncwarp();
       pl = plan_and_stage(c, cur);
@@ -489,55 +608,30 @@ __device__ __forceinline__ void l8_run_ragged(const Lines8Params& p, const uint3
     __syncwarp();
 
     if (lane < pl.count) {
-      const uint32_t i = c + lane;
       const uint32_t len = pl.len;
-      const uint32_t sh = pl.start & 15u;
+      const L8Align al(pl.start & 15u);
       const uint32_t c0 = pl.start >> 4;
-      const bool q1 = (sh & 4u) != 0, q2 = (sh & 8u) != 0;
-      const uint32_t r8 = (sh & 3u) * 8u;
       uint32_t e = p.root_entry;
       int32_t last = g.fwd.root_accepting ? 0 : -1;
       uint32_t tail_bit = g.fwd.root_accepting ? 1u : 0u;  // accept flag exactly at the end of the line (matches())
       uint4 x = lds_data16(cur + l8_rslot(c0));
-      for (uint32_t pos = 0; pos < len; pos += 16) {
-        const uint4 y = lds_data16(cur + l8_rslot(c0 + (pos >> 4) + 1));
-        // word select by the word part of the start offset, then funnel shift by its byte part
-        const uint32_t a0 = q2 ? x.z : x.x, a1 = q2 ? x.w : x.y, a2 = q2 ? y.x : x.z, a3 = q2 ? y.y : x.w;
-        const uint32_t a4 = q2 ? y.z : y.x, a5 = q2 ? y.w : y.y;
-        const uint32_t w0 = q1 ? a1 : a0, w1 = q1 ? a2 : a1, w2 = q1 ? a3 : a2, w3 = q1 ? a4 : a3, w4 = q1 ? a5 : a4;
+      for (uint32_t pos = 0; pos < len; pos += kPer) {
+        const uint4 y = lds_data16(cur + l8_rslot(c0 + (pos / kPer) + 1));
+        uint32_t w[4];
+        al.apply(x, y, w);
         uint32_t mask = 0;
-        l8_word(__funnelshift_r(w0, w1, r8), sel_a, sel_b, e, mask);
-        l8_word(__funnelshift_r(w1, w2, r8), sel_a, sel_b, e, mask);
-        l8_word(__funnelshift_r(w2, w3, r8), sel_a, sel_b, e, mask);
-        l8_word(__funnelshift_r(w3, w4, r8), sel_a, sel_b, e, mask);
-        const uint32_t valid = min(16u, len - pos);
-        mask >>= (16u - valid);  // drop the accept bits of chars past the end of the line
+        l8_word<CM>(w[0], cx, e, mask);
+        l8_word<CM>(w[1], cx, e, mask);
+        l8_word<CM>(w[2], cx, e, mask);
+        l8_word<CM>(w[3], cx, e, mask);
+        const uint32_t valid = min(kPer, len - pos);
+        mask >>= (kPer - valid);  // drop the accept bits of chars past the end of the line
         const int32_t cand = static_cast<int32_t>(pos + valid + 1) - __ffs(mask);
         last = mask ? cand : last;
         tail_bit = mask & 1u;
         x = y;
       }
-      if (g.mode == 0) {
-        bool m = tail_bit != 0;
-        if (g.min_length > 4 && static_cast<uint32_t>(g.min_length) > len) m = false;  // DFAMethodComponents.java:75-93
-        if (g.max_length != -1 && len > static_cast<uint32_t>(g.max_length)) m = false;
-        g.matched[i] = m;
-      } else if (g.mode == 1) {
-        g.matched[i] = last != -1;  // accepting rows of the containedIn automaton are absorbing
-      } else {
-        int32_t st = -1;
-        if (last != -1) {
-          if (g.reverse_mode == 2)
-            st = last - g.min_length;
-          else if (g.reverse_mode == 0 && p.has_bwd)
-            st = l8_reverse(p, [&](uint32_t ch) { return cur + l8_rslot(ch); }, pl.start, last, sel_a, sel_b, g.bwd.root_accepting != 0);
-          else
-            st = static_cast<int32_t>(dev_index_backwards<uint8_t>(g, data + g.offsets[i], last - 1, 0, 0x7fffffff));
-        }
-        g.matched[i] = last != -1;
-        g.start[i] = st;
-        g.end[i] = last;
-      }
+      l8_finish<CM, CharT>(p, cx, c + lane, len, last, tail_bit != 0, pl.start, [&](uint32_t ch) { return cur + l8_rslot(ch); });
     }
     __syncwarp();
     c = c_next;
@@ -547,6 +641,19 @@ __device__ __forceinline__ void l8_run_ragged(const Lines8Params& p, const uint3
     nxt = tmp;
   }
   cp_async_wait<0>();
+}
+
+template <int CM>
+__device__ __forceinline__ void l8_dispatch(const Lines8Params& p, const L8Ctx& cx, int log2cpl, uint32_t buf0, uint32_t buf1,
+                                            uint32_t lane, uint32_t warp_global, uint32_t n_warps) {
+  switch (log2cpl) {
+    case 0: l8_run<0, CM>(p, cx, buf0, buf1, lane, warp_global, n_warps); break;
+    case 1: l8_run<1, CM>(p, cx, buf0, buf1, lane, warp_global, n_warps); break;
+    case 2: l8_run<2, CM>(p, cx, buf0, buf1, lane, warp_global, n_warps); break;
+    case 3: l8_run<3, CM>(p, cx, buf0, buf1, lane, warp_global, n_warps); break;
+    case 4: l8_run<4, CM>(p, cx, buf0, buf1, lane, warp_global, n_warps); break;
+    default: l8_run_ragged<CM>(p, cx, buf0, buf1, lane, warp_global, n_warps); break;
+  }
 }
 
 __global__ void __launch_bounds__(kL8Threads, 1) lines8_kernel(const Lines8Params p) {
@@ -578,8 +685,10 @@ __global__ void __launch_bounds__(kL8Threads, 1) lines8_kernel(const Lines8Param
     tma_bulk_g2s(kL8AbsTrans, p.image + kL8CmapBytes, p.trans_bytes, kL8AbsBar);
   }
 
-  // --- line geometry: L from the first two offsets (uniform); every tile re-checks its own lines
-  const uint64_t L64 = g.offsets[1] - g.offsets[0];
+  // --- line geometry: byte length from the first two offsets (uniform); every tile re-checks its own lines
+  const uint32_t char_bytes = p.char_mode == kCmBytes ? 1u : 2u;
+  const uint64_t l_chars = g.offsets[1] - g.offsets[0];
+  const uint64_t L64 = l_chars * char_bytes;
   int log2cpl = -1;
   if (L64 >= 16 && L64 <= 256 && (L64 & (L64 - 1)) == 0) log2cpl = 31 - __clz(static_cast<uint32_t>(L64)) - 4;
   if (layout_ok) mbar_wait(kL8AbsBar, 0);  // table image has landed
@@ -590,22 +699,29 @@ __global__ void __launch_bounds__(kL8Threads, 1) lines8_kernel(const Lines8Param
   // length (its tiles still re-check themselves); everything else goes down the ragged path.
   if (log2cpl >= 0) {
     const uint32_t probe = static_cast<uint32_t>(min(static_cast<uint64_t>(lane) + 1, g.n - 1));
-    const bool same = g.offsets[probe + 1] - g.offsets[probe] == L64;
+    const bool same = g.offsets[probe + 1] - g.offsets[probe] == l_chars;
     if (!__all_sync(0xffffffffu, same)) log2cpl = -1;
   }
   if (!warp_ok) {
     // no room for this warp's buffers (unexpected shared-memory base): generic walk, one line per thread
-    for (uint64_t i = static_cast<uint64_t>(warp_global) * 32 + lane; i < g.n; i += static_cast<uint64_t>(n_warps) * 32) l8_slow_line(g, i);
+    for (uint64_t i = static_cast<uint64_t>(warp_global) * 32 + lane; i < g.n; i += static_cast<uint64_t>(n_warps) * 32) {
+      if (char_bytes == 1) l8_slow_line<uint8_t>(g, i);
+      else l8_slow_line<uint16_t>(g, i);
+    }
     return;
   }
-  switch (log2cpl) {
-    case 0: l8_run<0>(p, buf0, buf1, lane, warp_global, n_warps); break;
-    case 1: l8_run<1>(p, buf0, buf1, lane, warp_global, n_warps); break;
-    case 2: l8_run<2>(p, buf0, buf1, lane, warp_global, n_warps); break;
-    case 3: l8_run<3>(p, buf0, buf1, lane, warp_global, n_warps); break;
-    case 4: l8_run<4>(p, buf0, buf1, lane, warp_global, n_warps); break;
-    default: l8_run_ragged(p, buf0, buf1, lane, warp_global, n_warps); break;
-  }
+  L8Ctx cx;
+  cx.sel_a = 0x00010000u | (lane * 4);
+  cx.sel_b = cx.sel_a | 0x80u;
+  cx.page1 = static_cast<uint32_t>(p.mixed_page) << 8;
+  cx.page3 = static_cast<uint32_t>(p.mixed_page) << 24;
+  cx.ua = p.ua;
+  cx.ub = p.ub + (p.replicated == 32 ? lane * 4 : 0);
+  cx.xa = p.xa;
+  cx.xb = p.xb + (p.replicated == 32 ? lane * 4 : 0);
+  if (p.char_mode == kCmBytes) l8_dispatch<kCmBytes>(p, cx, log2cpl, buf0, buf1, lane, warp_global, n_warps);
+  else if (p.char_mode == kCmHi) l8_dispatch<kCmHi>(p, cx, log2cpl, buf0, buf1, lane, warp_global, n_warps);
+  else l8_dispatch<kCmMixed>(p, cx, log2cpl, buf0, buf1, lane, warp_global, n_warps);
 }
 
 }  // namespace ndl

@@ -103,8 +103,10 @@ __global__ void __launch_bounds__(kL8Threads, 1) long8_kernel(const Long8Params 
     const uint32_t c = lane + 32 * k;
     dst_off[k] = l8_slot(c >> LOG2CPL, c & 3, LOG2CPL) << 4;
   }
-  const uint32_t sel_a = 0x00010000u | (lane * 4);
-  const uint32_t sel_b = sel_a | 0x80u;
+  L8Ctx cx;
+  cx.sel_a = 0x00010000u | (lane * 4);
+  cx.sel_b = cx.sel_a | 0x80u;
+  cx.page1 = cx.page3 = cx.ua = cx.ub = cx.xa = cx.xb = 0;
   auto stage = [&](uint64_t t, uint32_t buf) {
     const uint8_t* src = p.data + t * 2048 + lane * 16;
 #pragma unroll
@@ -131,10 +133,10 @@ __global__ void __launch_bounds__(kL8Threads, 1) long8_kernel(const Long8Params 
       // 1. guess: 16 bytes before the segment, from the root
       if (lane != 0) pre = lds_data16(cur + (l8_slot(lane - 1, 3, LOG2CPL) << 4));
       uint32_t e = p.root_entry, mask = 0;
-      l8_word(pre.x, sel_a, sel_b, e, mask);
-      l8_word(pre.y, sel_a, sel_b, e, mask);
-      l8_word(pre.z, sel_a, sel_b, e, mask);
-      l8_word(pre.w, sel_a, sel_b, e, mask);
+      l8_word<kCmBytes>(pre.x, cx, e, mask);
+      l8_word<kCmBytes>(pre.y, cx, e, mask);
+      l8_word<kCmBytes>(pre.z, cx, e, mask);
+      l8_word<kCmBytes>(pre.w, cx, e, mask);
       if (lane == 0 && t == 0) e = p.entry0;  // the head was walked exactly
       const uint32_t guess = e & kL8FlagMask;
       // 2. the segment itself
@@ -143,10 +145,10 @@ __global__ void __launch_bounds__(kL8Threads, 1) long8_kernel(const Long8Params 
       for (uint32_t c = 0; c < 4; c++) {
         const uint4 w = lds_data16(cur + (l8_slot(lane, c, LOG2CPL) << 4));
         mask = 0;
-        l8_word(w.x, sel_a, sel_b, e, mask);
-        l8_word(w.y, sel_a, sel_b, e, mask);
-        l8_word(w.z, sel_a, sel_b, e, mask);
-        l8_word(w.w, sel_a, sel_b, e, mask);
+        l8_word<kCmBytes>(w.x, cx, e, mask);
+        l8_word<kCmBytes>(w.y, cx, e, mask);
+        l8_word<kCmBytes>(w.z, cx, e, mask);
+        l8_word<kCmBytes>(w.w, cx, e, mask);
         any |= mask;
       }
       const uint32_t exit_state = e & kL8FlagMask;

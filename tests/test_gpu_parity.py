@@ -265,3 +265,62 @@ def test_full_size_properties_c2():
     # matches()/containedIn() agree with find() where they must
     mc, _, _ = pat.match_batch(1, data, offsets)
     assert np.array_equal(mc, m)
+
+
+def utf16_lines(n, line_chars, seed, alphabet):
+    rng = np.random.default_rng(seed)
+    alpha = np.array([ord(ch) for ch in alphabet], dtype=np.uint16)
+    chars = alpha[rng.integers(0, len(alpha), size=n * line_chars)]
+    offsets = np.arange(n + 1, dtype=np.uint64) * np.uint64(line_chars)
+    return chars, offsets
+
+
+@pytest.mark.parametrize("line_chars", [8, 16, 32, 64, 128, 24, 5])
+def test_utf16_hi_byte_mode_fixed_lines(line_chars):
+    # class depends on the high byte only: [U+0600-06FF]+ (kCmHi)
+    chars, offsets = utf16_lines(6000, line_chars, line_chars, "abc xyz؀؁ۿ܀Ԁ✓")
+    assert_batch_equal(workloads.REGEX["c5"], 0, chars.view(np.uint8), offsets, cw=2)
+
+
+@pytest.mark.parametrize("line_chars", [8, 32, 64, 21])
+def test_utf16_mixed_page_mode(line_chars):
+    # ASCII patterns over UTF-16 text: page 0 is mixed, every other page is one class (kCmMixed)
+    chars, offsets = utf16_lines(6000, line_chars, 100 + line_chars, "0123456789-ab @.εΩд中İ1ı")
+    for regex in (workloads.REGEX["c2"], workloads.REGEX["c3"], "[0-9]+", "a.c", "b+@", r"\d+-\d+"):
+        assert_batch_equal(regex, 0, chars.view(np.uint8), offsets, cw=2)
+
+
+def test_utf16_ragged_and_unsupported_class_maps():
+    rng = np.random.default_rng(77)
+    alphabet = "0123456789-ab @.εΩλд中؀ۿ"
+    strings = ["".join(alphabet[j] for j in rng.integers(0, len(alphabet), int(rng.integers(0, 90)))) for _ in range(5000)]
+    data, offsets, cw = nb.pack_haystacks(strings, char_width=2)
+    for regex in (workloads.REGEX["c5"], workloads.REGEX["c3"], "[0-9]+", "ε|λ", "[a-bα-ω]+", "[؀-ۿ]+|[0-9]+", "a*"):
+        assert_batch_equal(regex, 0, data, offsets, cw)
+    for regex, fl in ((r"\w+", nb.UNICODE_CHARACTER_CLASS), ("[Γ-Θ]+", nb.CASE_INSENSITIVE | nb.UNICODE_CASE)):
+        assert_batch_equal(regex, fl, data, offsets, cw)
+
+
+def fast_path(pat, mode, cw):
+    L = _lib.lib()
+    L.ndl_debug_fast_path.argtypes = [__import__("ctypes").c_void_p, __import__("ctypes").c_int, __import__("ctypes").c_int]
+    v = L.ndl_debug_fast_path(pat._h, mode, cw)
+    if v < 0:
+        return None
+    return {"char_mode": v & 0xFF, "replicated": (v >> 8) & 0xFF, "has_bwd": (v >> 16) & 1, "n_cols": v >> 24}
+
+
+def test_expected_kernels_are_selected():
+    """Guards against silently falling back to the generic kernel on the BASELINE configs."""
+    fp = fast_path(pair(workloads.REGEX["c2"])[0], 2, 1)
+    assert fp == {"char_mode": 0, "replicated": 32, "has_bwd": 0, "n_cols": 3}
+    fp = fast_path(pair(workloads.REGEX["c3"])[0], 2, 1)
+    assert fp["char_mode"] == 0 and fp["replicated"] == 32 and fp["has_bwd"] == 1
+    fp = fast_path(pair(workloads.REGEX["c4"])[0], 2, 1)
+    assert fp["char_mode"] == 0 and fp["replicated"] == 1  # 258 rows: the pair table is not replicated
+    fp = fast_path(pair(workloads.REGEX["c5"])[0], 2, 2)
+    assert fp["char_mode"] == 1 and fp["replicated"] == 32 and fp["has_bwd"] == 1  # class from the high byte
+    fp = fast_path(pair(workloads.REGEX["c2"])[0], 2, 2)
+    assert fp["char_mode"] == 2  # ASCII pattern over UTF-16: one mixed page
+    assert fast_path(pair("[a-bα-ω]+")[0], 2, 2) is None  # two mixed pages: generic kernel
+    assert fast_path(pair("Holmes.{1,10}Watson|Watson.{1,10}Holmes")[0], 2, 1) is None  # 309 states x 12 classes
