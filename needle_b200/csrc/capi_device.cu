@@ -151,6 +151,7 @@ static int launch_batch(ndl_pattern* p, const BatchParams& bp, int char_width, u
     lp.xb = img.xb;
     lp.mixed_page = img.mixed_page;
     lp.replicated = img.replicated;
+    lp.row_bytes = img.row_bytes;
     lp.char_mode = img.char_mode;
     lp.has_bwd = img.has_bwd ? 1 : 0;
     uint64_t max_tiles = (bp.n + 1023) / 1024;  // a CTA's 32 warps take 32 lines each per round
@@ -241,8 +242,14 @@ int ndl_pattern_create(const uint8_t* blob, size_t blob_len, int device, ndl_pat
       const bool want_bwd = mode == NDL_MODE_FIND && p->cp.reverse_mode == kReverseTable;
       std::vector<uint8_t> img;
       Lines8Blob& b = cw == 1 ? p->l8[mode] : p->l16[mode];
-      bool ok = want_bwd && lines8_layout(fwd_t, &p->tables[kBackwards].host, cw, img, b);
-      if (!ok) ok = lines8_layout(fwd_t, nullptr, cw, img, b);  // reverse pass then walks the global tables
+      // preference: bank-replicated pair tables (with the BACKWARDS table resident when find() needs it),
+      // then - byte haystacks - the bank-replicated stride-1 layout, then unreplicated pair tables
+      const HostDeviceTable* bwd_t = want_bwd ? &p->tables[kBackwards].host : nullptr;
+      bool ok = want_bwd && lines8_layout(fwd_t, bwd_t, cw, false, img, b);
+      if (!ok) ok = lines8_layout(fwd_t, nullptr, cw, false, img, b);
+      if (!ok && cw == 1) ok = lines8_layout_s1(fwd_t, img, b);
+      if (!ok) ok = want_bwd && lines8_layout(fwd_t, bwd_t, cw, true, img, b);
+      if (!ok) ok = lines8_layout(fwd_t, nullptr, cw, true, img, b);
       if (!ok) continue;
       if (cudaMalloc(&b.dev, img.size()) != cudaSuccess ||
           cudaMemcpy(b.dev, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -382,7 +389,8 @@ int ndl_find_long(ndl_pattern* p, const void* data, uint64_t n_chars, int char_w
       last = r.last;
     }
   } else {
-    const uint32_t row_bytes = static_cast<uint32_t>(img.n_cols) * img.n_cols * 4u * img.replicated;
+    const bool s1 = img.char_mode == kCmBytes1;
+    const uint32_t row_bytes = img.row_bytes;
     // head: exact walk up to the first 2 KB boundary
     const uintptr_t a0 = reinterpret_cast<uintptr_t>(d_data) + static_cast<uintptr_t>(from);
     int64_t head_end = from + static_cast<int64_t>(((a0 + 2047) & ~static_cast<uintptr_t>(2047)) - a0);
@@ -415,15 +423,17 @@ int ndl_find_long(ndl_pattern* p, const void* data, uint64_t n_chars, int char_w
         lp.image = img.dev;
         lp.trans_bytes = img.trans_bytes;
         lp.root_entry = img.root_entry;
-        lp.entry0 = static_cast<uint32_t>(r.state) * row_bytes;
+        lp.row_bytes = row_bytes;
+        lp.entry0 = s1 ? static_cast<uint32_t>(r.state) : static_cast<uint32_t>(r.state) * row_bytes;
         lp.seam_guess = d_guess;
         lp.seam_exit = d_exit;
         lp.first_seg = &d_sc->first_seg;
         lp.first_bad = &d_sc->first_bad;
-        NDL_CUDA(cudaFuncSetAttribute(long8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kL8DynSmem));
+        auto kern = s1 ? long8_kernel<kCmBytes1> : long8_kernel<kCmBytes>;
+        NDL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kL8DynSmem));
         uint64_t want = (n_tiles + kL8Warps - 1) / kL8Warps;
         int blocks = static_cast<int>(want < static_cast<uint64_t>(p->sm_count) ? want : p->sm_count);
-        long8_kernel<<<blocks, kL8Threads, kL8DynSmem, stream>>>(lp);
+        kern<<<blocks, kL8Threads, kL8DynSmem, stream>>>(lp);
         g_launches.fetch_add(1);
         NDL_CUDA(cudaGetLastError());
         long8_seam_kernel<<<p->sm_count * 4, 256, 0, stream>>>(d_guess, d_exit, n_tiles, &d_sc->first_bad);
@@ -454,7 +464,7 @@ int ndl_find_long(ndl_pattern* p, const void* data, uint64_t n_chars, int char_w
           uint32_t exit_off = 0;
           NDL_CUDA(cudaMemcpyAsync(&exit_off, d_exit + (n_tiles - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
           NDL_CUDA(cudaStreamSynchronize(stream));
-          state = static_cast<int32_t>(exit_off / row_bytes);
+          state = static_cast<int32_t>(s1 ? exit_off : exit_off / row_bytes);
           pos = head_end + static_cast<int64_t>(n_tiles) * 2048;
         }
       }

@@ -62,6 +62,14 @@ constexpr uint32_t kL8MaxTransBytes = kL8AbsBar - kL8AbsTrans;  // 32704
 constexpr uint32_t kL8AbsEnd = kL8AbsBar + 16;
 constexpr uint32_t kL8DynSmem = kL8AbsEnd;  // covers the map for any dynamic base in [0, 0x400]
 constexpr uint32_t kL8FlagMask = 0x3fffffffu;
+// Second layout ("S1", for automata whose pair table cannot be replicated per bank, e.g. 256-state DFAs):
+// a 32 KB class map (128-byte slots) at 0x10000, then a stride-1 transition table of 16-bit entries,
+// replicated per lane (entry (row, col) is 64 B, lane l reads halfword l; two lanes share a bank word, which
+// is a broadcast, not a conflict), then the upper tile buffers.
+constexpr uint32_t kS1CmapBytes = 0x8000;
+constexpr uint32_t kS1AbsTrans = 0x18000;
+constexpr uint32_t kS1MaxTransBytes = 0x10800;  // 67584: 258 rows x 4 classes x 64 B fits
+constexpr uint32_t kS1UpperLo = kS1AbsTrans + kS1MaxTransBytes;  // 0x28800
 
 // Char modes.  The walk consumes 32-bit words of the haystack; what a "char" is depends on the mode:
 //   kCmBytes  char_width 1: four chars per word, class map indexed by the byte.
@@ -71,7 +79,8 @@ constexpr uint32_t kL8FlagMask = 0x3fffffffu;
 //             common class (an ASCII pattern over UTF-16 text): class map indexed by the LOW byte, and a
 //             select replaces the looked-up value by the common class when the high byte is another page.
 // Any other UTF-16 class map is left to the generic kernel.
-enum { kCmBytes = 0, kCmHi = 1, kCmMixed = 2 };
+//   kCmBytes1 char_width 1, ONE char per step over the S1 layout (see kS1* above).
+enum { kCmBytes = 0, kCmHi = 1, kCmMixed = 2, kCmBytes1 = 3 };
 
 // Device image for one (mode, char width): [cmap 64 KB][trans], plus what the kernel needs to start a walk.
 struct Lines8Blob {
@@ -83,6 +92,7 @@ struct Lines8Blob {
   uint32_t ua = 0, ub = 0;   // kCmMixed: CA / CB value of the class every other page has
   uint32_t xa = 0, xb = 0;   // UTF-16 modes: CA / CB value of the class of U+FFFF
   int mixed_page = 0;        // kCmMixed: the high byte of the non-uniform page
+  uint32_t row_bytes = 0;    // bytes per table row
   int char_mode = kCmBytes;
   int replicated = 0;        // 32 or 1
   int n_cols = 0;            // C
@@ -95,8 +105,8 @@ struct Lines8Blob {
 // columns are the distinct (forward class, backward class) combinations the class-map slots take.
 // Returns false when the class map has no supported char mode or the pair tables do not fit (the generic
 // kernel handles the pattern then).
-inline bool lines8_layout(const HostDeviceTable& f, const HostDeviceTable* b, int char_width, std::vector<uint8_t>& img,
-                          Lines8Blob& meta) {
+inline bool lines8_layout(const HostDeviceTable& f, const HostDeviceTable* b, int char_width, bool allow_unreplicated,
+                          std::vector<uint8_t>& img, Lines8Blob& meta) {
   using Key = std::pair<int, int>;
   auto key_of = [&](int c) { return Key{f.cmap[c], b ? b->cmap[c] : 0}; };
   Key slot_key[256];
@@ -146,7 +156,7 @@ inline bool lines8_layout(const HostDeviceTable& f, const HostDeviceTable* b, in
   int R;
   if (pairs * 128 <= static_cast<long>(kL8MaxTransBytes))
     R = 32;
-  else if (pairs * 4 <= static_cast<long>(kL8MaxTransBytes))
+  else if (allow_unreplicated && pairs * 4 <= static_cast<long>(kL8MaxTransBytes))
     R = 1;
   else
     return false;
@@ -188,12 +198,54 @@ inline bool lines8_layout(const HostDeviceTable& f, const HostDeviceTable* b, in
   meta.trans_bytes = trans_bytes;
   meta.replicated = R;
   meta.n_cols = C;
+  meta.row_bytes = row_bytes;
   meta.char_mode = char_mode;
   meta.mixed_page = mixed_page < 0 ? 0 : mixed_page;
   meta.ua = static_cast<uint32_t>(col_uniform) * C * col_bytes;
   meta.ub = kL8AbsTrans + static_cast<uint32_t>(col_uniform) * col_bytes;  // + lane*4 in the kernel when replicated
   meta.xa = static_cast<uint32_t>(col_exc) * C * col_bytes;
   meta.xb = kL8AbsTrans + static_cast<uint32_t>(col_exc) * col_bytes;
+  return true;
+}
+
+// The S1 image (byte haystacks, forward automaton only): [cmap 32 KB][trans u16].
+inline bool lines8_layout_s1(const HostDeviceTable& f, std::vector<uint8_t>& img, Lines8Blob& meta) {
+  std::vector<int> class_of_col, col_of_class(f.n_classes, -1);
+  int col_of_byte[256];
+  for (int v = 0; v < 256; v++) {
+    const int k = f.cmap[v];
+    if (col_of_class[k] < 0) {
+      col_of_class[k] = static_cast<int>(class_of_col.size());
+      class_of_col.push_back(k);
+    }
+    col_of_byte[v] = col_of_class[k];
+  }
+  const int C = static_cast<int>(class_of_col.size());
+  const int rows = f.n_states + 1;
+  if (rows > 0x7fff) return false;
+  const uint32_t row_bytes = static_cast<uint32_t>(C) * 64u;
+  const uint32_t trans_bytes = (static_cast<uint32_t>(rows) * row_bytes + 15) & ~15u;
+  if (trans_bytes > kS1MaxTransBytes) return false;
+  img.assign(kS1CmapBytes + trans_bytes, 0);
+  for (int v = 0; v < 256; v++)
+    for (uint32_t lane = 0; lane < 32; lane++) {
+      const uint32_t cm = kS1AbsTrans + static_cast<uint32_t>(col_of_byte[v]) * 64u + lane * 2u;
+      std::memcpy(img.data() + v * 128 + lane * 4, &cm, 4);
+    }
+  for (int s = 0; s < rows; s++)
+    for (int c = 0; c < C; c++) {
+      const int t = f.trans[static_cast<size_t>(s) * f.n_classes + class_of_col[c]];
+      const uint16_t e = static_cast<uint16_t>(t | (f.accept[t] ? 0x8000 : 0));
+      for (uint32_t lane = 0; lane < 32; lane++)
+        std::memcpy(img.data() + kS1CmapBytes + static_cast<uint32_t>(s) * row_bytes + static_cast<uint32_t>(c) * 64u + lane * 2u, &e, 2);
+    }
+  meta = Lines8Blob();
+  meta.trans_bytes = trans_bytes;
+  meta.root_entry = 0;
+  meta.replicated = 32;
+  meta.n_cols = C;
+  meta.row_bytes = row_bytes;
+  meta.char_mode = kCmBytes1;
   return true;
 }
 
@@ -207,6 +259,7 @@ struct Lines8Params {
   uint32_t xa, xb;       // UTF-16 modes: U+FFFF
   int mixed_page;
   int replicated;
+  uint32_t row_bytes;
   int char_mode;
   int has_bwd;  // BACKWARDS pair table resident: table-driven reverse pass runs on the staged tile
 };
@@ -264,6 +317,7 @@ struct L8Ctx {
   uint32_t page1, page3;  // kCmMixed: mixed page number positioned at byte 1 / byte 3 of a word
   uint32_t ua, ub;        // kCmMixed: CA / CB value of the common class of all other pages
   uint32_t xa, xb;        // UTF-16 modes: CA / CB value of U+FFFF, whose class never follows its page
+  uint32_t row_bytes;     // kCmBytes1
 };
 
 // One 2-char step.  KA / KB: byte index (within the 32-bit word) that selects the class-map slot of the
@@ -284,10 +338,30 @@ __device__ __forceinline__ void l8_step2(uint32_t word, const L8Ctx& cx, uint32_
   mask = __funnelshift_l(e, mask, 2);  // mask = mask << 2 | accept(1st) << 1 | accept(2nd)
 }
 
+__device__ __forceinline__ int32_t lds_tab_s16(uint32_t addr) {
+  int32_t v;
+  asm("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+// One 1-char step over the S1 layout on byte K of `word`: class-map slot address = 0x10000 | byte << 7 | lane*4,
+// entry = row index | accept << 15, loaded sign-extended so that the accept flag is the sign bit.
+template <int K>
+__device__ __forceinline__ void l8_step1(uint32_t word, const L8Ctx& cx, uint32_t& e, uint32_t& mask) {
+  const uint32_t sh = K == 0 ? (word << 7) : (word >> (8 * K - 7));
+  const uint32_t cm = lds_tab((sh & 0x7f80u) | cx.sel_a);
+  e = static_cast<uint32_t>(lds_tab_s16((e & 0x7fffu) * cx.row_bytes + cm));
+  mask = __funnelshift_l(e, mask, 1);
+}
+
 // All chars of one word, forwards / backwards.
 template <int CM>
 __device__ __forceinline__ void l8_word(uint32_t w, const L8Ctx& cx, uint32_t& e, uint32_t& mask) {
-  if (CM == kCmBytes) {
+  if (CM == kCmBytes1) {
+    l8_step1<0>(w, cx, e, mask);
+    l8_step1<1>(w, cx, e, mask);
+    l8_step1<2>(w, cx, e, mask);
+    l8_step1<3>(w, cx, e, mask);
+  } else if (CM == kCmBytes) {
     l8_step2<CM, 0, 1, 0, 0>(w, cx, e, mask);
     l8_step2<CM, 2, 3, 0, 0>(w, cx, e, mask);
   } else if (CM == kCmHi) {
@@ -298,7 +372,12 @@ __device__ __forceinline__ void l8_word(uint32_t w, const L8Ctx& cx, uint32_t& e
 }
 template <int CM>
 __device__ __forceinline__ void l8_word_rev(uint32_t w, const L8Ctx& cx, uint32_t& e, uint32_t& mask) {
-  if (CM == kCmBytes) {
+  if (CM == kCmBytes1) {  // (no BACKWARDS table is resident in the S1 layout; kept for completeness)
+    l8_step1<3>(w, cx, e, mask);
+    l8_step1<2>(w, cx, e, mask);
+    l8_step1<1>(w, cx, e, mask);
+    l8_step1<0>(w, cx, e, mask);
+  } else if (CM == kCmBytes) {
     l8_step2<CM, 3, 2, 0, 0>(w, cx, e, mask);
     l8_step2<CM, 1, 0, 0, 0>(w, cx, e, mask);
   } else if (CM == kCmHi) {
@@ -309,7 +388,7 @@ __device__ __forceinline__ void l8_word_rev(uint32_t w, const L8Ctx& cx, uint32_
 }
 template <int CM>
 struct L8Chars {
-  static constexpr int kBytes = CM == kCmBytes ? 1 : 2;   // bytes per char
+  static constexpr int kBytes = (CM == kCmBytes || CM == kCmBytes1) ? 1 : 2;   // bytes per char
   static constexpr int kPerChunk = 16 / kBytes;           // chars (= accept bits) per 16-byte chunk
 };
 
@@ -433,7 +512,7 @@ template <int LOG2CPL, int CM>
 __device__ __forceinline__ void l8_run(const Lines8Params& p, const L8Ctx& cx, const uint32_t buf0, const uint32_t buf1,
                                        const uint32_t lane, const uint32_t warp_global, const uint32_t n_warps) {
   using G = L8Geom<LOG2CPL>;
-  using CharT = typename std::conditional<CM == kCmBytes, uint8_t, uint16_t>::type;
+  using CharT = typename std::conditional<L8Chars<CM>::kBytes == 1, uint8_t, uint16_t>::type;
   constexpr uint32_t kCharBytes = L8Chars<CM>::kBytes;
   constexpr uint32_t kPer = L8Chars<CM>::kPerChunk;
   constexpr uint32_t kLenChars = G::kL / kCharBytes;
@@ -546,7 +625,7 @@ __device__ __forceinline__ uint32_t l8_rslot(uint32_t c) { return (c ^ ((c >> 3)
 template <int CM>
 __device__ __forceinline__ void l8_run_ragged(const Lines8Params& p, const L8Ctx& cx, const uint32_t buf0, const uint32_t buf1,
                                               const uint32_t lane, const uint32_t warp_global, const uint32_t n_warps) {
-  using CharT = typename std::conditional<CM == kCmBytes, uint8_t, uint16_t>::type;
+  using CharT = typename std::conditional<L8Chars<CM>::kBytes == 1, uint8_t, uint16_t>::type;
   constexpr uint32_t kCharBytes = L8Chars<CM>::kBytes;
   constexpr uint32_t kPer = L8Chars<CM>::kPerChunk;
   const BatchParams& g = p.g;
@@ -656,21 +735,39 @@ __device__ __forceinline__ void l8_dispatch(const Lines8Params& p, const L8Ctx& 
   }
 }
 
+// Where a warp's two tile buffers live.  Buffer slots (2 KB) fill the space below the class map and an
+// "upper" region that depends on the layout; warp w owns slots 2w and 2w+1.  Warps without a pair of
+// slots (one warp in the S1 layout) do not take part.
+struct L8Setup {
+  bool layout_ok, warp_ok;
+  uint32_t buf0, buf1, usable_warps, cmap_bytes, abs_trans;
+  __device__ __forceinline__ L8Setup(bool s1, uint32_t warp) {
+    extern __shared__ __align__(128) uint8_t l8_dyn_smem[];
+    const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(l8_dyn_smem));
+    const uint32_t buf_a = (base + 127) & ~127u;
+    layout_ok = buf_a <= 0x8000;
+    cmap_bytes = s1 ? kS1CmapBytes : kL8CmapBytes;
+    abs_trans = s1 ? kS1AbsTrans : kL8AbsTrans;
+    const uint32_t upper_lo = s1 ? kS1UpperLo : kL8AbsSet1;
+    const uint32_t upper_hi = s1 ? kL8AbsBar : kL8AbsTrans;
+    const uint32_t fit = layout_ok ? (kL8AbsCmap - buf_a) / kL8WarpBuf : 0;
+    const uint32_t slots = fit + (upper_hi - upper_lo) / kL8WarpBuf;
+    usable_warps = min(static_cast<uint32_t>(kL8Warps), slots / 2);
+    warp_ok = layout_ok && warp < usable_warps;
+    auto slot = [&](uint32_t k) { return k < fit ? buf_a + k * kL8WarpBuf : upper_lo + (k - fit) * kL8WarpBuf; };
+    buf0 = slot(2 * warp);
+    buf1 = slot(2 * warp + 1);
+  }
+};
+
 __global__ void __launch_bounds__(kL8Threads, 1) lines8_kernel(const Lines8Params p) {
-  extern __shared__ __align__(128) uint8_t l8_dyn_smem[];
-  const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(l8_dyn_smem));
   const uint32_t tid = threadIdx.x;
   const uint32_t lane = tid & 31, warp = tid >> 5;
   const BatchParams& g = p.g;
 
-  // set-0 buffers fill the space between the start of dynamic shared memory and the class map; the ones
-  // that do not fit (one, when the base is 0x400) live in the spill area
-  const uint32_t buf_a = (base + 127) & ~127u;
-  const bool layout_ok = buf_a <= 0x8000;
-  const uint32_t fit = layout_ok ? (kL8AbsCmap - buf_a) / kL8WarpBuf : 0;
-  const bool warp_ok = layout_ok && (warp < fit || warp - fit < (kL8AbsTrans - kL8AbsSpill) / kL8WarpBuf);
-  const uint32_t buf0 = warp < fit ? buf_a + warp * kL8WarpBuf : kL8AbsSpill + (warp - fit) * kL8WarpBuf;
-  const uint32_t buf1 = kL8AbsSet1 + warp * kL8WarpBuf;
+  L8Setup su(p.char_mode == kCmBytes1, warp);
+  const bool layout_ok = su.layout_ok, warp_ok = su.warp_ok;
+  const uint32_t buf0 = su.buf0, buf1 = su.buf1;
 
   // --- table image: two TMA bulk copies (cmap, trans) completing on one mbarrier
   if (tid == 0) {
@@ -680,21 +777,21 @@ __global__ void __launch_bounds__(kL8Threads, 1) lines8_kernel(const Lines8Param
   }
   __syncthreads();
   if (tid == 0 && layout_ok) {
-    mbar_expect_tx(kL8AbsBar, kL8CmapBytes + p.trans_bytes);
-    tma_bulk_g2s(kL8AbsCmap, p.image, kL8CmapBytes, kL8AbsBar);
-    tma_bulk_g2s(kL8AbsTrans, p.image + kL8CmapBytes, p.trans_bytes, kL8AbsBar);
+    mbar_expect_tx(kL8AbsBar, su.cmap_bytes + p.trans_bytes);
+    tma_bulk_g2s(kL8AbsCmap, p.image, su.cmap_bytes, kL8AbsBar);
+    tma_bulk_g2s(su.abs_trans, p.image + su.cmap_bytes, p.trans_bytes, kL8AbsBar);
   }
 
   // --- line geometry: byte length from the first two offsets (uniform); every tile re-checks its own lines
-  const uint32_t char_bytes = p.char_mode == kCmBytes ? 1u : 2u;
+  const uint32_t char_bytes = (p.char_mode == kCmBytes || p.char_mode == kCmBytes1) ? 1u : 2u;
   const uint64_t l_chars = g.offsets[1] - g.offsets[0];
   const uint64_t L64 = l_chars * char_bytes;
   int log2cpl = -1;
   if (L64 >= 16 && L64 <= 256 && (L64 & (L64 - 1)) == 0) log2cpl = 31 - __clz(static_cast<uint32_t>(L64)) - 4;
   if (layout_ok) mbar_wait(kL8AbsBar, 0);  // table image has landed
 
-  const uint32_t warp_global = blockIdx.x * kL8Warps + warp;
-  const uint32_t n_warps = gridDim.x * kL8Warps;
+  const uint32_t warp_global = blockIdx.x * su.usable_warps + warp;
+  const uint32_t n_warps = gridDim.x * su.usable_warps;
   // The fixed-length path is taken when the batch starts with 33 equally spaced offsets of a supported
   // length (its tiles still re-check themselves); everything else goes down the ragged path.
   if (log2cpl >= 0) {
@@ -702,14 +799,16 @@ __global__ void __launch_bounds__(kL8Threads, 1) lines8_kernel(const Lines8Param
     const bool same = g.offsets[probe + 1] - g.offsets[probe] == l_chars;
     if (!__all_sync(0xffffffffu, same)) log2cpl = -1;
   }
-  if (!warp_ok) {
-    // no room for this warp's buffers (unexpected shared-memory base): generic walk, one line per thread
-    for (uint64_t i = static_cast<uint64_t>(warp_global) * 32 + lane; i < g.n; i += static_cast<uint64_t>(n_warps) * 32) {
+  if (!layout_ok) {
+    // unexpected shared-memory base: generic walk, one line per thread
+    for (uint64_t i = (static_cast<uint64_t>(blockIdx.x) * kL8Warps + warp) * 32 + lane; i < g.n;
+         i += static_cast<uint64_t>(gridDim.x) * kL8Threads) {
       if (char_bytes == 1) l8_slow_line<uint8_t>(g, i);
       else l8_slow_line<uint16_t>(g, i);
     }
     return;
   }
+  if (!warp_ok) return;  // no pair of tile buffers for this warp in this layout
   L8Ctx cx;
   cx.sel_a = 0x00010000u | (lane * 4);
   cx.sel_b = cx.sel_a | 0x80u;
@@ -719,7 +818,9 @@ __global__ void __launch_bounds__(kL8Threads, 1) lines8_kernel(const Lines8Param
   cx.ub = p.ub + (p.replicated == 32 ? lane * 4 : 0);
   cx.xa = p.xa;
   cx.xb = p.xb + (p.replicated == 32 ? lane * 4 : 0);
-  if (p.char_mode == kCmBytes) l8_dispatch<kCmBytes>(p, cx, log2cpl, buf0, buf1, lane, warp_global, n_warps);
+  cx.row_bytes = p.row_bytes;
+  if (p.char_mode == kCmBytes1) l8_dispatch<kCmBytes1>(p, cx, log2cpl, buf0, buf1, lane, warp_global, n_warps);
+  else if (p.char_mode == kCmBytes) l8_dispatch<kCmBytes>(p, cx, log2cpl, buf0, buf1, lane, warp_global, n_warps);
   else if (p.char_mode == kCmHi) l8_dispatch<kCmHi>(p, cx, log2cpl, buf0, buf1, lane, warp_global, n_warps);
   else l8_dispatch<kCmMixed>(p, cx, log2cpl, buf0, buf1, lane, warp_global, n_warps);
 }

@@ -64,37 +64,34 @@ struct Long8Params {
   const uint8_t* image;    // lines8 image of the FORWARDS table
   uint32_t trans_bytes;
   uint32_t root_entry;
-  uint32_t entry0;         // exact entry of tile 0, lane 0 (pair-table row offset)
+  uint32_t row_bytes;      // kCmBytes1 layout
+  uint32_t entry0;         // exact entry of tile 0, lane 0 (same encoding as the table entries, flags clear)
   uint32_t* seam_guess;    // [n_tiles] lane 0's guessed entry
   uint32_t* seam_exit;     // [n_tiles] lane 31's exit
   unsigned long long* first_seg;   // atomicMin: first segment (global index) that saw an accepting state
   unsigned long long* first_bad;   // atomicMin: first segment whose in-warp check failed
 };
 
+template <int CM>
 __global__ void __launch_bounds__(kL8Threads, 1) long8_kernel(const Long8Params p) {
-  extern __shared__ __align__(128) uint8_t l8_dyn_smem[];
-  const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(l8_dyn_smem));
   const uint32_t tid = threadIdx.x;
   const uint32_t lane = tid & 31, warp = tid >> 5;
-  const uint32_t buf_a = (base + 127) & ~127u;
-  const bool layout_ok = buf_a <= 0x8000;
-  const uint32_t fit = layout_ok ? (kL8AbsCmap - buf_a) / kL8WarpBuf : 0;
-  const uint32_t buf0 = warp < fit ? buf_a + warp * kL8WarpBuf : kL8AbsSpill + (warp - fit) * kL8WarpBuf;
-  const uint32_t buf1 = kL8AbsSet1 + warp * kL8WarpBuf;
+  L8Setup su(CM == kCmBytes1, warp);
+  const uint32_t buf0 = su.buf0, buf1 = su.buf1;
   if (tid == 0) {
     mbar_init(kL8AbsBar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  if (!layout_ok) {  // cannot happen with the launch configuration used; report every tile as unverified
+  if (!su.layout_ok) {  // cannot happen with the launch configuration used; report every tile as unverified
     if (tid == 0 && blockIdx.x == 0) atomicMin(p.first_bad, 0ull);
     return;
   }
   if (tid == 0) {
-    mbar_expect_tx(kL8AbsBar, kL8CmapBytes + p.trans_bytes);
-    tma_bulk_g2s(kL8AbsCmap, p.image, kL8CmapBytes, kL8AbsBar);
-    tma_bulk_g2s(kL8AbsTrans, p.image + kL8CmapBytes, p.trans_bytes, kL8AbsBar);
+    mbar_expect_tx(kL8AbsBar, su.cmap_bytes + p.trans_bytes);
+    tma_bulk_g2s(kL8AbsCmap, p.image, su.cmap_bytes, kL8AbsBar);
+    tma_bulk_g2s(su.abs_trans, p.image + su.cmap_bytes, p.trans_bytes, kL8AbsBar);
   }
   constexpr int LOG2CPL = 2;  // 64-byte segments
   uint32_t dst_off[4];
@@ -107,17 +104,19 @@ __global__ void __launch_bounds__(kL8Threads, 1) long8_kernel(const Long8Params 
   cx.sel_a = 0x00010000u | (lane * 4);
   cx.sel_b = cx.sel_a | 0x80u;
   cx.page1 = cx.page3 = cx.ua = cx.ub = cx.xa = cx.xb = 0;
+  cx.row_bytes = p.row_bytes;
   auto stage = [&](uint64_t t, uint32_t buf) {
     const uint8_t* src = p.data + t * 2048 + lane * 16;
 #pragma unroll
     for (uint32_t k = 0; k < 4; k++) cp_async16(buf + dst_off[k], src + 512 * k);
     cp_async_commit();
   };
-  const uint64_t n_warps = static_cast<uint64_t>(gridDim.x) * kL8Warps;
-  uint64_t t = static_cast<uint64_t>(blockIdx.x) * kL8Warps + warp;
+  const uint64_t n_warps = static_cast<uint64_t>(gridDim.x) * su.usable_warps;
+  uint64_t t = static_cast<uint64_t>(blockIdx.x) * su.usable_warps + warp;
   uint32_t cur = buf0, nxt = buf1;
-  if (t < p.n_tiles) stage(t, cur);
   mbar_wait(kL8AbsBar, 0);
+  if (!su.warp_ok) return;  // no pair of tile buffers for this warp in this layout
+  if (t < p.n_tiles) stage(t, cur);
 
   for (; t < p.n_tiles; t += n_warps) {
     if (t + n_warps < p.n_tiles) stage(t + n_warps, nxt);
@@ -133,25 +132,26 @@ __global__ void __launch_bounds__(kL8Threads, 1) long8_kernel(const Long8Params 
       // 1. guess: 16 bytes before the segment, from the root
       if (lane != 0) pre = lds_data16(cur + (l8_slot(lane - 1, 3, LOG2CPL) << 4));
       uint32_t e = p.root_entry, mask = 0;
-      l8_word<kCmBytes>(pre.x, cx, e, mask);
-      l8_word<kCmBytes>(pre.y, cx, e, mask);
-      l8_word<kCmBytes>(pre.z, cx, e, mask);
-      l8_word<kCmBytes>(pre.w, cx, e, mask);
+      l8_word<CM>(pre.x, cx, e, mask);
+      l8_word<CM>(pre.y, cx, e, mask);
+      l8_word<CM>(pre.z, cx, e, mask);
+      l8_word<CM>(pre.w, cx, e, mask);
       if (lane == 0 && t == 0) e = p.entry0;  // the head was walked exactly
-      const uint32_t guess = e & kL8FlagMask;
+      constexpr uint32_t kStateMask = CM == kCmBytes1 ? 0x7fffu : kL8FlagMask;
+      const uint32_t guess = e & kStateMask;
       // 2. the segment itself
       uint32_t any = 0;
 #pragma unroll
       for (uint32_t c = 0; c < 4; c++) {
         const uint4 w = lds_data16(cur + (l8_slot(lane, c, LOG2CPL) << 4));
         mask = 0;
-        l8_word<kCmBytes>(w.x, cx, e, mask);
-        l8_word<kCmBytes>(w.y, cx, e, mask);
-        l8_word<kCmBytes>(w.z, cx, e, mask);
-        l8_word<kCmBytes>(w.w, cx, e, mask);
+        l8_word<CM>(w.x, cx, e, mask);
+        l8_word<CM>(w.y, cx, e, mask);
+        l8_word<CM>(w.z, cx, e, mask);
+        l8_word<CM>(w.w, cx, e, mask);
         any |= mask;
       }
-      const uint32_t exit_state = e & kL8FlagMask;
+      const uint32_t exit_state = e & kStateMask;
       // 3. in-warp check + seams
       const uint32_t prev_exit = __shfl_up_sync(0xffffffffu, exit_state, 1);
       const bool bad = lane != 0 && prev_exit != guess;

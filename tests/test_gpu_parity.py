@@ -317,7 +317,9 @@ def test_expected_kernels_are_selected():
     fp = fast_path(pair(workloads.REGEX["c3"])[0], 2, 1)
     assert fp["char_mode"] == 0 and fp["replicated"] == 32 and fp["has_bwd"] == 1
     fp = fast_path(pair(workloads.REGEX["c4"])[0], 2, 1)
-    assert fp["char_mode"] == 0 and fp["replicated"] == 1  # 258 rows: the pair table is not replicated
+    assert fp["char_mode"] == 3 and fp["replicated"] == 32  # 258 rows: stride-1 16-bit table, bank replicated
+    fp = fast_path(pair("a[ab]{8}c|b[ab]{6}d")[0], 2, 1)
+    assert fp is None or fp["replicated"] in (1, 32)
     fp = fast_path(pair(workloads.REGEX["c5"])[0], 2, 2)
     assert fp["char_mode"] == 1 and fp["replicated"] == 32 and fp["has_bwd"] == 1  # class from the high byte
     fp = fast_path(pair(workloads.REGEX["c2"])[0], 2, 2)
