@@ -71,6 +71,10 @@ struct ndl_pattern {
   Lines8Blob l16[3];  // per mode: same for UTF-16 haystacks (when the class map has a supported char mode)
   std::mutex ws_mutex;
   Workspace ws;
+  // host-buffer calls are pipelined in chunks: H2D on s_h2d, kernels on the caller's stream, D2H on s_d2h
+  static constexpr int kMaxChunks = 16;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_h2d[kMaxChunks] = {}, ev_kernel[kMaxChunks] = {};
 };
 
 namespace ndl {
@@ -97,6 +101,11 @@ static void free_pattern(ndl_pattern* p) {
   }
   for (auto& b : p->l8) cudaFree(b.dev);
   for (auto& b : p->l16) cudaFree(b.dev);
+  if (p->s_h2d) cudaStreamDestroy(p->s_h2d);
+  if (p->s_d2h) cudaStreamDestroy(p->s_d2h);
+  if (p->ev_start) cudaEventDestroy(p->ev_start);
+  for (auto& e : p->ev_h2d) if (e) cudaEventDestroy(e);
+  for (auto& e : p->ev_kernel) if (e) cudaEventDestroy(e);
   cudaFree(p->ws.data);
   cudaFree(p->ws.offsets);
   cudaFree(p->ws.from);
@@ -309,24 +318,64 @@ int ndl_match_batch(ndl_pattern* p, int mode, const void* data, const uint64_t* 
   Workspace& ws = p->ws;
   int rc = ensure_workspace(ws, data_bytes + 64, n, from != nullptr, mode == NDL_MODE_FIND);
   if (rc != NDL_OK) return rc;
-  if (data_bytes)
-    NDL_CUDA(cudaMemcpyAsync(ws.data, static_cast<const uint8_t*>(data) + base * char_width, data_bytes, cudaMemcpyHostToDevice, stream));
-  NDL_CUDA(cudaMemcpyAsync(ws.offsets, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
-  if (from) NDL_CUDA(cudaMemcpyAsync(ws.from, from, n * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+  if (!p->s_h2d) {
+    NDL_CUDA(cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
+    NDL_CUDA(cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));
+    NDL_CUDA(cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming));
+    for (int k = 0; k < ndl_pattern::kMaxChunks; k++) {
+      NDL_CUDA(cudaEventCreateWithFlags(&p->ev_h2d[k], cudaEventDisableTiming));
+      NDL_CUDA(cudaEventCreateWithFlags(&p->ev_kernel[k], cudaEventDisableTiming));
+    }
+  }
   // the staged copy starts at offsets[0]; bias the data pointer instead of rewriting the offsets
   bp.data = static_cast<const uint8_t*>(ws.data) - base * char_width;
-  bp.offsets = ws.offsets;
-  bp.from = from ? ws.from : nullptr;
-  bp.matched = ws.matched;
-  bp.start = ws.start;
-  bp.end = ws.end;
-  rc = launch_batch(p, bp, char_width, total_chars, stream);
-  if (rc != NDL_OK) return rc;
-  NDL_CUDA(cudaMemcpyAsync(matched, ws.matched, n, cudaMemcpyDeviceToHost, stream));
-  if (mode == NDL_MODE_FIND) {
-    NDL_CUDA(cudaMemcpyAsync(start, ws.start, n * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-    NDL_CUDA(cudaMemcpyAsync(end, ws.end, n * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  // chunks of about 64 MB of haystack (at most kMaxChunks), cut at line boundaries
+  int n_chunks = static_cast<int>(data_bytes / (64u << 20)) + 1;
+  if (n_chunks > ndl_pattern::kMaxChunks) n_chunks = ndl_pattern::kMaxChunks;
+  if (static_cast<uint64_t>(n_chunks) > n) n_chunks = static_cast<int>(n);
+  NDL_CUDA(cudaEventRecord(p->ev_start, stream));
+  NDL_CUDA(cudaStreamWaitEvent(p->s_h2d, p->ev_start, 0));
+  NDL_CUDA(cudaStreamWaitEvent(p->s_d2h, p->ev_start, 0));
+  uint64_t i0 = 0;
+  for (int k = 0; k < n_chunks; k++) {
+    uint64_t i1 = n;
+    if (k + 1 < n_chunks) {
+      const uint64_t target = base + total_chars * static_cast<uint64_t>(k + 1) / static_cast<uint64_t>(n_chunks);
+      uint64_t a = i0 + 1, b = n;  // first line index >= i0 + 1 whose offset reaches the target
+      while (a < b) {
+        const uint64_t m = (a + b) / 2;
+        if (offsets[m] < target) a = m + 1; else b = m;
+      }
+      i1 = a;
+    }
+    const uint64_t cnt = i1 - i0;
+    const size_t c0 = static_cast<size_t>(offsets[i0] - base) * char_width, c1 = static_cast<size_t>(offsets[i1] - base) * char_width;
+    NDL_CUDA(cudaMemcpyAsync(ws.offsets + i0, offsets + i0, (cnt + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, p->s_h2d));
+    if (c1 > c0)
+      NDL_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(ws.data) + c0, static_cast<const uint8_t*>(data) + base * char_width + c0, c1 - c0,
+                               cudaMemcpyHostToDevice, p->s_h2d));
+    if (from) NDL_CUDA(cudaMemcpyAsync(ws.from + i0, from + i0, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, p->s_h2d));
+    NDL_CUDA(cudaEventRecord(p->ev_h2d[k], p->s_h2d));
+    NDL_CUDA(cudaStreamWaitEvent(stream, p->ev_h2d[k], 0));
+    BatchParams cb = bp;
+    cb.n = cnt;
+    cb.offsets = ws.offsets + i0;
+    cb.from = from ? ws.from + i0 : nullptr;
+    cb.matched = ws.matched + i0;
+    cb.start = ws.start + i0;
+    cb.end = ws.end + i0;
+    rc = launch_batch(p, cb, char_width, 0, stream);
+    if (rc != NDL_OK) return rc;
+    NDL_CUDA(cudaEventRecord(p->ev_kernel[k], stream));
+    NDL_CUDA(cudaStreamWaitEvent(p->s_d2h, p->ev_kernel[k], 0));
+    NDL_CUDA(cudaMemcpyAsync(matched + i0, ws.matched + i0, cnt, cudaMemcpyDeviceToHost, p->s_d2h));
+    if (mode == NDL_MODE_FIND) {
+      NDL_CUDA(cudaMemcpyAsync(start + i0, ws.start + i0, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, p->s_d2h));
+      NDL_CUDA(cudaMemcpyAsync(end + i0, ws.end + i0, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, p->s_d2h));
+    }
+    i0 = i1;
   }
+  NDL_CUDA(cudaStreamSynchronize(p->s_d2h));
   NDL_CUDA(cudaStreamSynchronize(stream));
   return NDL_OK;
 }
