@@ -269,7 +269,7 @@ def run_ours(args, rank, local_rank, world):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(args.workload) if n == default_lines else None,
-                         "kernel": "lines8_kernel" if cw == 1 else "generic_batch_kernel<uint16_t>", "kernel_ms": kernel_ms, "peak_source": peak_src,
+                         "kernel": "lines8_kernel", "kernel_ms": kernel_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": in_bytes,
                          "note": "algorithmic bytes = haystack bytes only (SURVEY.md 8d); the launch also reads 8 B/line of offsets and writes 9 B/line of results"},
         }
@@ -281,74 +281,118 @@ def run_ours(args, rank, local_rank, world):
 
 
 def run_long(args, rank, local_rank, world):
-    """BASELINE configs[3]: 256-state DFA over ONE 8 GiB haystack, find() start/end offsets (ndl_find_long).
-    The buffer is {a,b} noise with the only match in its last 9 bytes, so the whole buffer must be scanned."""
+    """BASELINE configs[3]: 256-state DFA over ONE 8 GiB haystack, find() start/end offsets.  The buffer is {a,b}
+    noise with the only match in its last 9 bytes, so the whole buffer must be scanned.  N = 1: ndl_find_long.
+    N > 1: the haystack is split into N contiguous chunks, one per GPU (strong scaling: the same 8 GiB in total),
+    and needle_b200.sharding.find_long_sharded runs the entry-state guess / all-gather / verify protocol over
+    ndl_find_long_from (one 40-byte NCCL all-gather per step on the data path)."""
     import torch
 
     import needle_b200 as nb
     from needle_b200 import _lib
+    from needle_b200 import sharding
 
-    if world != 1:
-        if rank == 0:
-            print(json.dumps({"metric": METRIC, "unavailable": "c4long: the multi-GPU exchange for one haystack is not built; run with --gpus 1"}))
-        return
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
     regex = workloads.REGEX["c4"]
-    n = args.lines or (8 << 30)
-    blob = nb.compile_to_bytes(regex, 0)
+    n_total = args.lines or (8 << 30)
+    base, top = n_total * rank // world, n_total * (rank + 1) // world
+    n = top - base
+    blob = nb.compile_to_bytes(regex, 0) if rank == 0 else None
+    if dist:
+        blob = sharding.broadcast_blob(blob, src=0, device=dev)
     pat = nb.Pattern(blob, device=local_rank)
     g = torch.Generator(device="cuda")
-    g.manual_seed(0x5EED0004)
+    g.manual_seed(0x5EED0004 + rank)
     data = torch.randint(ord("a"), ord("b") + 1, (n,), dtype=torch.uint8, device="cuda", generator=g)
-    data[n - 9:] = torch.tensor(list(b"abababbac"), dtype=torch.uint8, device="cuda")
+    if rank == world - 1:
+        data[n - 9:] = torch.tensor(list(b"abababbac"), dtype=torch.uint8, device="cuda")
     stream = torch.cuda.current_stream()
+    want = (True, n_total - 9, n_total)
 
-    def step():
-        return pat.find_long_ptrs(data.data_ptr(), n, 1, 0, nb.MEM_DEVICE, stream.cuda_stream)
+    if world == 1:
+        def step():
+            return pat.find_long_ptrs(data.data_ptr(), n, 1, 0, nb.MEM_DEVICE, stream.cuda_stream)
+    else:
+        halo = sharding.exchange_halo(data[n - sharding.HALO:], device=dev)  # once: the haystack does not change
+        allgather = sharding.tensor_allgather(dev)
+        fd, bd = pat.forwards_state_count, pat.backwards_state_count
 
-    for _ in range(args.warmup):
+        def step():
+            return sharding.find_long_sharded(
+                lambda entry: pat.find_long_from(data.data_ptr(), n, entry, mem_kind=nb.MEM_DEVICE, stream=stream.cuda_stream),
+                lambda index, entry, li: pat.find_long_back(data.data_ptr(), n, index, entry, li, mem_kind=nb.MEM_DEVICE, stream=stream.cuda_stream),
+                lambda: pat.find_long_from(halo.ctypes.data, halo.size, 0, mem_kind=nb.MEM_HOST, stream=stream.cuda_stream)[1],
+                base, n, rank, world, allgather, fd, bd, pat.reverse_mode, pat.min_length, pat.backwards_root_accepting)
+
+    def sync_all():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    res = None
+    for _ in range(max(1, args.warmup)):
         res = step()
-    if res != (True, n - 9, n):
-        raise SystemExit(f"bench: ndl_find_long returned {res}, expected {(True, n - 9, n)}")
+    if res != want:
+        raise SystemExit(f"bench: find over the long haystack returned {res}, expected {want}")
     sampler = ClockSampler(local_rank)
     launches0 = _lib.lib().ndl_kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
+    sync_all()
     sampler.start()
+    t0 = time.perf_counter()
     ev0.record(stream)
     for _ in range(args.steps):
         step()
     ev1.record(stream)
-    torch.cuda.synchronize()
+    sync_all()
+    wall_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop()
-    ms = ev0.elapsed_time(ev1)
+    ms = max(ev0.elapsed_time(ev1), wall_ms if world > 1 else 0.0)  # the multi-rank step has host-side hand-overs
     launches = _lib.lib().ndl_kernel_launches() - launches0
-    # end to end from pinned host memory on a 1 GiB prefix-sized buffer (same content law)
+    # end to end from pinned host memory on a (at most) 1 GiB buffer per rank (same content law)
     ne = min(n, 1 << 30)
-    host = data[n - ne:].cpu().pin_memory()
-    pat.find_long_ptrs(host.data_ptr(), ne, 1, 0, nb.MEM_HOST, stream.cuda_stream)
-    t0 = time.perf_counter()
-    e2e_steps = 3
-    for _ in range(e2e_steps):
-        r = pat.find_long_ptrs(host.data_ptr(), ne, 1, 0, nb.MEM_HOST, stream.cuda_stream)
-    e2e_s = time.perf_counter() - t0
-    assert r == (True, ne - 9, ne)
-    peak, peak_src = measured_peak_gbs()
-    value = n * args.steps / (ms * 1e-3) / 1e9
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[3]: 256-state DFA 'a[ab]{7}c', ONE haystack, find() start/end (int64), match in the last 9 bytes",
-                   "regex": regex, "mode": "find", "haystack_bytes": n, "l2": "haystack larger than L2"},
-        "matches_per_s": args.steps / (ms * 1e-3),
-        "e2e": {"value": ne * e2e_steps / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": ne, "d2h_bytes_per_step": 17, "steps": e2e_steps,
-                "note": f"host path measured on a {ne >> 20} MiB haystack"},
-        "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": value, "peak": peak, "unit": "GB/s", "frac": value / peak, "traffic": None,
-                     "kernel": "long8_kernel (+ head/tail/seam helper kernels inside the timed call)", "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": n},
-    }
-    print(json.dumps(line), flush=True)
+    e2e_steps, e2e_s = 3, None
+    if world == 1:
+        host = data[n - ne:].cpu().pin_memory()
+        pat.find_long_ptrs(host.data_ptr(), ne, 1, 0, nb.MEM_HOST, stream.cuda_stream)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            r = pat.find_long_ptrs(host.data_ptr(), ne, 1, 0, nb.MEM_HOST, stream.cuda_stream)
+        e2e_s = time.perf_counter() - t0
+        assert r == (True, ne - 9, ne)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms = float(t.item())
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        value = n_total * args.steps / (ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[3]: 256-state DFA 'a[ab]{7}c', ONE haystack, find() start/end (int64), match in the last 9 bytes",
+                       "regex": regex, "mode": "find", "haystack_bytes": n_total, "l2": "haystack larger than L2",
+                       "sharding": "one contiguous chunk per rank; entry-state guess from a 16-byte halo, one all-gather of (entry, end, exit) per step"},
+            "matches_per_s": args.steps / (ms * 1e-3),
+            "gpu_launches": int(tot.item()), "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": value / world, "peak": peak, "unit": "GB/s", "frac": value / world / peak, "traffic": None,
+                         "kernel": "long8_kernel (+ head/tail/seam helper kernels inside the timed call)", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": n},
+        }
+        if e2e_s is not None:
+            line["e2e"] = {"value": ne * e2e_steps / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": ne, "d2h_bytes_per_step": 17,
+                           "steps": e2e_steps, "note": f"host path measured on a {ne >> 20} MiB haystack"}
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
 
 
 def measured_traffic(workload):

@@ -30,7 +30,8 @@ class BlobInfo(ctypes.Structure):
 SYMBOLS = (
     "ndl_compile", "ndl_compile_utf8", "ndl_blob_free", "ndl_blob_info_get", "ndl_pattern_create",
     "ndl_pattern_destroy", "ndl_match_batch", "ndl_find_long", "ndl_last_error", "ndl_version",
-    "ndl_device_count", "ndl_kernel_launches", "ndl_pattern_device",
+    "ndl_device_count", "ndl_kernel_launches", "ndl_pattern_device", "ndl_find_long_from", "ndl_forwards_state_count",
+    "ndl_find_long_back", "ndl_backwards_state_count", "ndl_backwards_root_accepting", "ndl_reverse_mode", "ndl_min_length",
 )
 
 _lib = None
@@ -65,6 +66,16 @@ def lib():
     L.ndl_find_long.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int64,
                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
     L.ndl_find_long.restype = ctypes.c_int
+    L.ndl_find_long_from.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int64, ctypes.c_int32,
+                                     ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                     ctypes.c_void_p]
+    L.ndl_find_long_from.restype = ctypes.c_int
+    L.ndl_find_long_back.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+                                     ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    L.ndl_find_long_back.restype = ctypes.c_int
+    for f in ("ndl_forwards_state_count", "ndl_backwards_state_count", "ndl_backwards_root_accepting", "ndl_reverse_mode", "ndl_min_length"):
+        getattr(L, f).argtypes = [ctypes.c_void_p]
+        getattr(L, f).restype = ctypes.c_int
     L.ndl_last_error.restype = ctypes.c_char_p
     L.ndl_version.restype = ctypes.c_char_p
     L.ndl_device_count.restype = ctypes.c_int

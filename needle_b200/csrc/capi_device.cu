@@ -380,12 +380,15 @@ int ndl_match_batch(ndl_pattern* p, int mode, const void* data, const uint64_t* 
   return NDL_OK;
 }
 
-int ndl_find_long(ndl_pattern* p, const void* data, uint64_t n_chars, int char_width, int64_t from, uint8_t* matched,
-                  int64_t* start, int64_t* end, int mem_kind, void* stream_) {
+}  // extern "C"
+
+static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, int char_width, int64_t from, int32_t entry_state,
+                          int64_t last_init, uint8_t* matched, int64_t* start, int64_t* end, int32_t* exit_state, int mem_kind,
+                          void* stream_) {
   if (!p) return fail(NDL_EINVAL, "pattern must not be NULL");
   if (char_width != 1 && char_width != 2) return fail(NDL_EINVAL, "char_width must be 1 or 2");
   if (mem_kind != NDL_MEM_HOST && mem_kind != NDL_MEM_DEVICE) return fail(NDL_EINVAL, "mem_kind must be NDL_MEM_HOST or NDL_MEM_DEVICE");
-  if (!matched || !start || !end) return fail(NDL_EINVAL, "matched, start and end must not be NULL");
+  if (!matched || !end || (!start && !exit_state)) return fail(NDL_EINVAL, "matched, start and end must not be NULL");
   if (from < 0) return fail(NDL_EINVAL, "from must be >= 0");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   NDL_CUDA(cudaSetDevice(p->device));
@@ -426,15 +429,22 @@ int ndl_find_long(ndl_pattern* p, const void* data, uint64_t n_chars, int char_w
   int64_t last = -1;
   int rc = NDL_OK;
   SeqResult r;
+  r.state = entry_state;
+  r.last = last_init;
+  r.pos = from;
+  if (entry_state < 0 || entry_state > dead) return fail(NDL_EINVAL, "entry_state out of range");
   const bool root_acc = p->tables[kForwards].host.root_accepting;
   const Lines8Blob& img = p->l8[NDL_MODE_FIND];
-  const bool fast = char_width == 1 && !root_acc && img.ok && from < n;
+  // the chunk-parallel path is for the search phase (no match seen yet) of a pattern with a non-accepting root
+  const bool fast = char_width == 1 && !root_acc && img.ok && from < n && last_init == -1 && entry_state != dead;
 
   if (!fast) {
-    // plain sequential walk (accepting root, UTF-16, or no shared-memory image): DFAClassBuilder.java:335-471
-    last = root_acc ? (from < n ? from : 0) : -1;
-    if (from < n) {
-      if ((rc = seq(from, n, 0, from, last, r)) != NDL_OK) return rc;
+    // plain sequential walk (accepting root, UTF-16, no shared-memory image, or continuing a match that is
+    // already under way): DFAClassBuilder.java:335-471
+    last = last_init;
+    if (root_acc && entry_state == 0 && last_init == -1) last = from < n ? from : 0;
+    if (from < n && entry_state != dead) {
+      if ((rc = seq(from, n, entry_state, from, last, r)) != NDL_OK) return rc;
       last = r.last;
     }
   } else {
@@ -444,7 +454,7 @@ int ndl_find_long(ndl_pattern* p, const void* data, uint64_t n_chars, int char_w
     const uintptr_t a0 = reinterpret_cast<uintptr_t>(d_data) + static_cast<uintptr_t>(from);
     int64_t head_end = from + static_cast<int64_t>(((a0 + 2047) & ~static_cast<uintptr_t>(2047)) - a0);
     if (head_end > n) head_end = n;
-    if ((rc = seq(from, head_end, 0, from, -1, r)) != NDL_OK) return rc;
+    if ((rc = seq(from, head_end, entry_state, from, -1, r)) != NDL_OK) return rc;
     bool done = false;
     if (r.state == dead) {
       last = r.last;
@@ -453,6 +463,7 @@ int ndl_find_long(ndl_pattern* p, const void* data, uint64_t n_chars, int char_w
       SeqResult r2;
       if ((rc = seq(head_end, n, r.state, head_end, r.last, r2)) != NDL_OK) return rc;
       last = r2.last;
+      r = r2;
       done = true;
     }
     if (!done) {
@@ -529,7 +540,7 @@ int ndl_find_long(ndl_pattern* p, const void* data, uint64_t n_chars, int char_w
   if (last != -1) {
     if (p->cp.reverse_mode == kReverseFixedLength) {
       st = last - p->cp.min_length;
-    } else {
+    } else if (start) {
       BatchParams bp;
       std::memset(&bp, 0, sizeof(bp));
       bp.reverse_mode = p->cp.reverse_mode;
@@ -546,16 +557,80 @@ int ndl_find_long(ndl_pattern* p, const void* data, uint64_t n_chars, int char_w
     }
   }
   const uint8_t m = last != -1;
+  if (exit_state) *exit_state = r.state;  // state after the last char that was read (DEAD when the walk died)
   if (mem_kind == NDL_MEM_HOST) {
     *matched = m;
-    *start = st;
+    if (start) *start = st;
     *end = last;
   } else {
     NDL_CUDA(cudaMemcpyAsync(matched, &m, 1, cudaMemcpyHostToDevice, stream));
-    NDL_CUDA(cudaMemcpyAsync(start, &st, sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+    if (start) NDL_CUDA(cudaMemcpyAsync(start, &st, sizeof(int64_t), cudaMemcpyHostToDevice, stream));
     NDL_CUDA(cudaMemcpyAsync(end, &last, sizeof(int64_t), cudaMemcpyHostToDevice, stream));
     NDL_CUDA(cudaStreamSynchronize(stream));
   }
+  return NDL_OK;
+}
+
+extern "C" {
+
+int ndl_find_long(ndl_pattern* p, const void* data, uint64_t n_chars, int char_width, int64_t from, uint8_t* matched,
+                  int64_t* start, int64_t* end, int mem_kind, void* stream) {
+  return find_long_impl(p, data, n_chars, char_width, from, 0, -1, matched, start, end, nullptr, mem_kind, stream);
+}
+
+int ndl_find_long_from(ndl_pattern* p, const void* data, uint64_t n_chars, int char_width, int64_t from, int32_t entry_state,
+                       int64_t last_init, uint8_t* matched, int64_t* start, int64_t* end, int32_t* exit_state, int mem_kind,
+                       void* stream) {
+  return find_long_impl(p, data, n_chars, char_width, from, entry_state, last_init, matched, start, end, exit_state, mem_kind, stream);
+}
+
+int ndl_forwards_state_count(const ndl_pattern* p) { return p ? p->tables[kForwards].host.n_states : -1; }
+int ndl_backwards_state_count(const ndl_pattern* p) { return p ? p->tables[kBackwards].host.n_states : -1; }
+int ndl_backwards_root_accepting(const ndl_pattern* p) { return p && p->tables[kBackwards].host.root_accepting ? 1 : 0; }
+int ndl_reverse_mode(const ndl_pattern* p) { return p ? p->cp.reverse_mode : -1; }
+int ndl_min_length(const ndl_pattern* p) { return p ? p->cp.min_length : -1; }
+
+int ndl_find_long_back(ndl_pattern* p, const void* data, uint64_t n_chars, int char_width, int64_t index, int64_t lower,
+                       int32_t entry_state, int64_t last_init, int64_t* start, int32_t* exit_state, int mem_kind, void* stream_) {
+  if (!p) return fail(NDL_EINVAL, "pattern must not be NULL");
+  if (char_width != 1 && char_width != 2) return fail(NDL_EINVAL, "char_width must be 1 or 2");
+  if (mem_kind != NDL_MEM_HOST && mem_kind != NDL_MEM_DEVICE) return fail(NDL_EINVAL, "mem_kind must be NDL_MEM_HOST or NDL_MEM_DEVICE");
+  if (!start || !exit_state) return fail(NDL_EINVAL, "start and exit_state must not be NULL");
+  if (p->cp.reverse_mode == kReverseFixedLength) return fail(NDL_EINVAL, "fixed-length pattern: start = end - min_length, no reverse pass");
+  const int dead = p->tables[kBackwards].host.n_states;
+  if (entry_state < 0 || entry_state > dead) return fail(NDL_EINVAL, "entry_state out of range");
+  if (lower < 0 || index >= static_cast<int64_t>(n_chars)) return fail(NDL_EINVAL, "index / lower out of range");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NDL_CUDA(cudaSetDevice(p->device));
+  std::lock_guard<std::mutex> lock(p->ws_mutex);
+  const uint8_t* d_data = static_cast<const uint8_t*>(data);
+  if (mem_kind == NDL_MEM_HOST && index >= lower) {
+    // only s[lower, index] is read: stage that window
+    const size_t w0 = static_cast<size_t>(lower) * char_width, w1 = static_cast<size_t>(index + 1) * char_width;
+    int rc = ensure_workspace(p->ws, w1 - w0 + 64, 16, false, true);
+    if (rc != NDL_OK) return rc;
+    NDL_CUDA(cudaMemcpyAsync(p->ws.data, static_cast<const uint8_t*>(data) + w0, w1 - w0, cudaMemcpyHostToDevice, stream));
+    d_data = static_cast<const uint8_t*>(p->ws.data) - w0;
+  }
+  int64_t* d_out = nullptr;
+  NDL_CUDA(cudaMalloc(&d_out, 2 * sizeof(int64_t)));
+  struct Guard { void* a; ~Guard() { cudaFree(a); } } guard{d_out};
+  BatchParams bp;
+  std::memset(&bp, 0, sizeof(bp));
+  bp.reverse_mode = p->cp.reverse_mode;
+  bp.reverse_char = p->cp.reverse_char;
+  bp.bwd = p->tables[kBackwards].view();
+  if (char_width == 1)
+    seq_back_from_kernel<uint8_t><<<1, 32, 0, stream>>>(bp, d_data, index, lower, entry_state, last_init, d_out);
+  else
+    seq_back_from_kernel<uint16_t><<<1, 32, 0, stream>>>(bp, reinterpret_cast<const uint16_t*>(d_data), index, lower, entry_state, last_init, d_out);
+  g_launches.fetch_add(1);
+  NDL_CUDA(cudaGetLastError());
+  int64_t h[2];
+  NDL_CUDA(cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  NDL_CUDA(cudaStreamSynchronize(stream));
+  *start = h[0];
+  *exit_state = static_cast<int32_t>(h[1]);
   return NDL_OK;
 }
 

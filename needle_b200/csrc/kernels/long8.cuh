@@ -58,6 +58,35 @@ __global__ void seq_back_kernel(BatchParams g, const CharT* s, int64_t index, in
   *out = dev_index_backwards<CharT>(g, s, index, lower, int_max);
 }
 
+// The same loop from an arbitrary BACKWARDS state (one rank's part of a reverse pass that crosses chunk
+// boundaries): scans s[lower, index] downwards; out[0] = smallest accepting index or last_init, out[1] = exit state
+// (n_states = DEAD; single-char form: 0 = not found yet, n_states = found).
+template <typename CharT>
+__global__ void seq_back_from_kernel(BatchParams g, const CharT* s, int64_t index, int64_t lower, int32_t state0, int64_t last_init,
+                                     int64_t* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int dead = g.bwd.n_states;
+  int64_t last = last_init;
+  int state = state0;
+  if (g.reverse_mode == 1) {
+    state = 0;
+    for (; index >= lower; index--)
+      if (static_cast<int>(s[index]) == g.reverse_char) {
+        last = index;
+        state = dead;
+        break;
+      }
+  } else {
+    for (; state != dead && index >= lower; index--) {
+      state = dev_step(g.bwd, state, s[index]);
+      if (state == dead) break;
+      if (__ldg(g.bwd.accept + state)) last = index;
+    }
+  }
+  out[0] = last;
+  out[1] = state;
+}
+
 struct Long8Params {
   const uint8_t* data;     // 2048-byte aligned start of tile 0
   uint64_t n_tiles;        // full 2 KB tiles

@@ -29,6 +29,9 @@ ALL_FLAGS = DOTALL | CASE_INSENSITIVE | UNICODE_CASE | LEFTMOST_LONGEST | UNICOD
 INT_MAX = 0x7FFFFFFF
 
 
+NO_START = 2 ** 63 - 1  # "no accepting index yet" of a reverse scan (the reference uses Integer.MAX_VALUE)
+
+
 class PatternException(RuntimeError):
     """com.justinblank.strings.PatternException"""
 
@@ -220,6 +223,59 @@ class Pattern:
         if rc != _lib.NDL_OK:
             _raise(rc, "ndl_find_long")
         return bool(m.value), st.value, en.value
+
+    def find_long_from(self, data_ptr: int, n_chars: int, entry_state: int = 0, char_width: int = 1, from_: int = 0,
+                       mem_kind: int = _lib.MEM_HOST, stream: int = 0):
+        """Forward scan of one rank's chunk of a haystack split across GPUs (ndl_find_long_from), started in
+        `entry_state` of the FORWARDS automaton.  Returns (end, exit_state): `end` = chunk-local index after the last
+        accepting step or -1, `exit_state` = state after the last char read (forwards_state_count = dead)."""
+        ex = ctypes.c_int32()
+        if mem_kind == _lib.MEM_DEVICE:
+            import torch
+            out = torch.zeros(1, dtype=torch.int64, device=f"cuda:{self.device}")
+            mm = torch.zeros(1, dtype=torch.uint8, device=f"cuda:{self.device}")
+            rc = _lib.lib().ndl_find_long_from(self._h, data_ptr or None, n_chars, char_width, from_, entry_state, -1,
+                                               mm.data_ptr(), None, out.data_ptr(), ctypes.byref(ex), mem_kind, stream or None)
+            if rc != _lib.NDL_OK:
+                _raise(rc, "ndl_find_long_from")
+            return int(out.item()), ex.value
+        m, en = ctypes.c_uint8(), ctypes.c_int64()
+        rc = _lib.lib().ndl_find_long_from(self._h, data_ptr or None, n_chars, char_width, from_, entry_state, -1,
+                                           ctypes.byref(m), None, ctypes.byref(en), ctypes.byref(ex), mem_kind, stream or None)
+        if rc != _lib.NDL_OK:
+            _raise(rc, "ndl_find_long_from")
+        return en.value, ex.value
+
+    def find_long_back(self, data_ptr: int, n_chars: int, index: int, entry_state: int = 0, last_init: int = NO_START,
+                       char_width: int = 1, lower: int = 0, mem_kind: int = _lib.MEM_HOST, stream: int = 0):
+        """Reverse scan of one rank's chunk (ndl_find_long_back) over [lower, index] downwards from `entry_state` of
+        the BACKWARDS automaton.  Returns (start, exit_state): smallest accepting chunk-local index or last_init."""
+        st, ex = ctypes.c_int64(), ctypes.c_int32()
+        rc = _lib.lib().ndl_find_long_back(self._h, data_ptr or None, n_chars, char_width, index, lower, entry_state, last_init,
+                                           ctypes.byref(st), ctypes.byref(ex), mem_kind, stream or None)
+        if rc != _lib.NDL_OK:
+            _raise(rc, "ndl_find_long_back")
+        return st.value, ex.value
+
+    @property
+    def forwards_state_count(self) -> int:
+        return _lib.lib().ndl_forwards_state_count(self._h)
+
+    @property
+    def backwards_state_count(self) -> int:
+        return _lib.lib().ndl_backwards_state_count(self._h)
+
+    @property
+    def backwards_root_accepting(self) -> bool:
+        return bool(_lib.lib().ndl_backwards_root_accepting(self._h))
+
+    @property
+    def reverse_mode(self) -> int:
+        return _lib.lib().ndl_reverse_mode(self._h)
+
+    @property
+    def min_length(self) -> int:
+        return _lib.lib().ndl_min_length(self._h)
 
     def find_all(self, strings: Sequence[Union[str, bytes]]):
         """Convenience: first find() per string.  Returns list of (matched, start, end)."""

@@ -56,6 +56,127 @@ def broadcast_blob(blob: Optional[bytes], src: int = 0, device=None) -> bytes:
     return bytes(buf.cpu().numpy().tobytes())
 
 
+# ----------------------------------------------------------------------------------------------------------
+# One haystack split across ranks (BASELINE config 4 on several GPUs; SURVEY.md section 8(e), second row).
+#
+# Rank r holds the contiguous chunk [base_r, base_r + n_r).  The forward scan of a chunk needs the automaton state
+# at its first char, which depends on everything before it.  The protocol needs one small all-gather per round:
+#
+#   forward  round 0: every rank r > 0 GUESSES its entry state (the scan, from the root, of the `HALO` chars before
+#            its chunk - the tail of rank r-1, exchanged once), rank 0 starts in the root; all ranks scan at once.
+#            The (entry, end, exit) records are all-gathered and every rank resolves them the same way, walking
+#            the ranks in order from the root: a record is VERIFIED when its entry equals the exit of the verified
+#            record before it.  The walk stops at the first unverified record - that rank scans again from the now
+#            known state and another round runs - or when the automaton has died / the ranks are exhausted: the
+#            end of the match is the last accepting index seen on the verified path (indexForwards,
+#            DFAClassBuilder.java:335-471).  A search automaton forgets (long8.cuh), so round 0 normally suffices;
+#            in the worst case (`a.*c`) every round verifies one more rank, like a sequential hand-over.
+#   reverse  fixed-length patterns: start = end - minLength (:640-646).  Otherwise indexBackwards(end - 1, 0)
+#            (:529-614) starts on the rank that holds end - 1 and is handed to the rank before it for as long as
+#            the BACKWARDS automaton is still alive at a chunk boundary (one all-gather per hand-over).
+#
+# `scan(entry_state) -> (end_local | -1, exit_state)` and `scan_back(index_local, entry_state, last_init_local) ->
+# (start_local | NO_START, exit_state)` are the per-rank primitives: Pattern.find_long_from / find_long_back on a
+# GPU, the oracle's scan_from / scan_back_from in the CPU tests.
+# ----------------------------------------------------------------------------------------------------------
+HALO = 16
+NO_START = 2 ** 63 - 1
+
+
+def resolve_forward(records, dead_state):
+    """Pure step of the forward protocol.  records[r] = (entry, end_local, exit, base).  Returns
+    ("done", end_global | -1) or ("rescan", rank, entry_state)."""
+    state, end = 0, -1
+    for r, (entry, end_local, exit_state, base) in enumerate(records):
+        if state == dead_state:
+            break
+        if entry != state:
+            return "rescan", r, state
+        if end_local != -1:
+            end = base + end_local
+        state = exit_state
+    return "done", end
+
+
+def find_long_sharded(scan, scan_back, guess_entry, base, n_local, rank, world_size, allgather, fwd_dead, bwd_dead,
+                      reverse_mode, min_length, bwd_root_accepting):
+    """find() of one haystack whose chunk [base, base + n_local) lives on this rank.  Every rank returns the same
+    (matched, start, end) in global indices.  `allgather(obj)` returns the list of every rank's obj."""
+    entry = 0 if rank == 0 else guess_entry()
+    rec = None
+    end = -1
+    for _ in range(world_size + 1):
+        if rec is None or rec[0] != entry:
+            # (rank 0 always scans: an accepting root matches the empty haystack, DFAClassBuilder.java:356)
+            end_local, exit_state = scan(entry) if (n_local > 0 or rank == 0) else (-1, entry)
+            rec = (int(entry), int(end_local), int(exit_state), int(base))
+        verdict = resolve_forward(allgather(rec), fwd_dead)
+        if verdict[0] == "done":
+            end = verdict[1]
+            break
+        if verdict[1] == rank:
+            entry = verdict[2]
+    else:
+        raise RuntimeError("find_long_sharded: forward phase did not converge")
+    if end == -1:
+        return False, -1, -1
+    if reverse_mode == 2:
+        return True, end - min_length, end
+
+    # reverse pass: (state, smallest accepting index so far, next index to read), handed down rank by rank
+    state, start, index = 0, (0 if (bwd_root_accepting and reverse_mode == 0) else NO_START), end - 1
+    bases = allgather((int(base), int(n_local)))
+    for r in range(world_size - 1, -1, -1):
+        b, n = bases[r]
+        if n == 0 or index < b or index >= b + n:
+            continue  # this rank holds nothing of [.., index]
+        if rank == r:
+            li = start - b if start != NO_START else NO_START
+            s_local, state = scan_back(index - b, state, li)
+            start = s_local + b if s_local != NO_START else NO_START
+        state, start = allgather((int(state), int(start)) if rank == r else None)[r]
+        index = b - 1
+        if state == bwd_dead or index < 0:
+            break
+    return True, start, end
+
+
+def tensor_allgather(device=None):
+    """An `allgather(obj)` for find_long_sharded over torch.distributed: obj is None or a tuple of up to 4 ints,
+    moved as one int64[5] all-gather (NCCL over NVLink on GPUs, gloo on CPU)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size()
+    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
+                                              if dist.get_backend() == "nccl" else torch.device("cpu"))
+
+    def allgather(obj):
+        vals = [0, 0, 0, 0, 0]
+        if obj is not None:
+            vals[0] = len(obj)
+            vals[1:1 + len(obj)] = [int(v) for v in obj]
+        mine = torch.tensor(vals, dtype=torch.int64, device=dev)
+        out = torch.empty(world * 5, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(out, mine)
+        rows = out.cpu().view(world, 5).tolist()
+        return [tuple(r[1:1 + r[0]]) if r[0] else None for r in rows]
+    return allgather
+
+
+def exchange_halo(tail, device=None):
+    """Every rank contributes the last HALO bytes of its chunk (a uint8 tensor of exactly HALO entries, zero padded
+    at the front if the chunk is shorter); returns the tail of the rank before this one as a numpy array."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(), dist.get_rank()
+    out = torch.empty(world * HALO, dtype=torch.uint8, device=tail.device)
+    dist.all_gather_into_tensor(out, tail.contiguous())
+    prev = out.view(world, HALO)[rank - 1] if rank > 0 else out.view(world, HALO)[0][:0]
+    return prev.cpu().numpy()
+
+
 def gather_results(matched: np.ndarray, start: Optional[np.ndarray], end: Optional[np.ndarray], dst: int = 0):
     """Optional: collect per-rank result slices on `dst` in rank order (not on the timed path)."""
     import torch.distributed as dist

@@ -32,6 +32,13 @@ def lib():
         L.ndlo_index_backwards.argtypes = [vp, vp, ctypes.c_int, i64, i64, i64]
         L.ndlo_index_backwards.restype = i64
         L.ndlo_find.argtypes = [vp, vp, i64, ctypes.c_int, i64, i64, ctypes.POINTER(i64), ctypes.POINTER(i64)]
+        L.ndlo_scan_from.argtypes = [vp, vp, i64, ctypes.c_int, i64, ctypes.c_int32, i64, ctypes.POINTER(ctypes.c_int32)]
+        L.ndlo_scan_from.restype = i64
+        L.ndlo_forwards_state_count.argtypes = [vp]
+        L.ndlo_scan_back_from.argtypes = [vp, vp, ctypes.c_int, i64, i64, ctypes.c_int32, i64, ctypes.POINTER(ctypes.c_int32)]
+        L.ndlo_scan_back_from.restype = i64
+        L.ndlo_backwards_state_count.argtypes = [vp]
+        L.ndlo_backwards_root_accepting.argtypes = [vp]
         L.ndlo_match_batch.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_uint64, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int]
         _lib = L
     return _lib
@@ -111,6 +118,31 @@ class Oracle:
             out.append((st, en))
             prev, frm = (st, en), en
         return out
+
+    def scan_from(self, data, entry_state=0, last_init=-1, from_=0, cw=1):
+        """(last, exit_state) of the forward scan of a chunk from an arbitrary state (multi-rank protocol check)."""
+        data = np.ascontiguousarray(data).view(np.uint8)
+        ex = ctypes.c_int32()
+        last = lib().ndlo_scan_from(self._h, data.ctypes.data if data.size else None, data.size // cw, cw, from_, entry_state,
+                                    last_init, ctypes.byref(ex))
+        return last, ex.value
+
+    def forwards_state_count(self):
+        return lib().ndlo_forwards_state_count(self._h)
+
+    def scan_back_from(self, data, index, entry_state=0, last_init=2 ** 63 - 1, lower=0, cw=1):
+        """(start, exit_state) of the reverse scan of chunk[lower, index] from an arbitrary BACKWARDS state."""
+        data = np.ascontiguousarray(data).view(np.uint8)
+        ex = ctypes.c_int32()
+        st = lib().ndlo_scan_back_from(self._h, data.ctypes.data if data.size else None, cw, index, lower, entry_state, last_init,
+                                       ctypes.byref(ex))
+        return st, ex.value
+
+    def backwards_state_count(self):
+        return lib().ndlo_backwards_state_count(self._h)
+
+    def backwards_root_accepting(self):
+        return bool(lib().ndlo_backwards_root_accepting(self._h))
 
     # -- batches
     def match_batch(self, mode, data, offsets, char_width=1, from_=None, threads=1):
