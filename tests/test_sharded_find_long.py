@@ -229,7 +229,7 @@ def test_gpu_chunks_match_sequential_find(regex, alphabet, plants):
         if regex.startswith("a[ab]"):
             data[data == ord("c")] = ord("b")
         for pl in plants:
-            if n > len(pl):
+            if n - len(pl) > n // 2:
                 pos = int(rng.integers(n // 2, n - len(pl)))
                 data[pos:pos + len(pl)] = np.frombuffer(pl, dtype=np.uint8)
         want = oracle_find_long(ora, data)
