@@ -269,7 +269,7 @@ def run_ours(args, rank, local_rank, world):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(args.workload) if n == default_lines else None,
-                         "kernel": "lines8_kernel", "kernel_ms": kernel_ms, "peak_source": peak_src,
+                         "kernel": kernel_name(pat, cw), "kernel_ms": kernel_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": in_bytes,
                          "note": "algorithmic bytes = haystack bytes only (SURVEY.md 8d); the launch also reads 8 B/line of offsets and writes 9 B/line of results"},
         }
@@ -393,6 +393,16 @@ def run_long(args, rank, local_rank, world):
         print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()
+
+
+def kernel_name(pat, cw):
+    import ctypes
+
+    from needle_b200 import _lib
+    L = _lib.lib()
+    L.ndl_debug_kernel_name.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    L.ndl_debug_kernel_name.restype = ctypes.c_char_p
+    return L.ndl_debug_kernel_name(pat._h, 2, cw).decode()
 
 
 def measured_traffic(workload):

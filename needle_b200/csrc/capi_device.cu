@@ -69,6 +69,8 @@ struct ndl_pattern {
   DeviceTableStorage tables[4];
   Lines8Blob l8[3];   // per mode: shared-memory image of the lines8 kernel for byte haystacks
   Lines8Blob l16[3];  // per mode: same for UTF-16 haystacks (when the class map has a supported char mode)
+  Lines8Blob q8[3];   // per mode: SWAR image (linesq_kernel) for byte haystacks, when the class map has a plan
+  Lines8Blob q16[3];  // per mode: same for UTF-16 haystacks
   std::mutex ws_mutex;
   Workspace ws;
   // host-buffer calls are pipelined in chunks: H2D on s_h2d, kernels on the caller's stream, D2H on s_d2h
@@ -101,6 +103,8 @@ static void free_pattern(ndl_pattern* p) {
   }
   for (auto& b : p->l8) cudaFree(b.dev);
   for (auto& b : p->l16) cudaFree(b.dev);
+  for (auto& b : p->q8) cudaFree(b.dev);
+  for (auto& b : p->q16) cudaFree(b.dev);
   if (p->s_h2d) cudaStreamDestroy(p->s_h2d);
   if (p->s_d2h) cudaStreamDestroy(p->s_d2h);
   if (p->ev_start) cudaEventDestroy(p->ev_start);
@@ -141,28 +145,59 @@ static int ensure_workspace(Workspace& ws, size_t data_bytes, uint64_t n, bool w
   return NDL_OK;
 }
 
+// The linesq_kernel instantiation of a SWAR char mode (nullptr: not instantiated).
+typedef void (*LinesqKernel)(const Lines8Params);
+static LinesqKernel linesq_kernel_for(int cm) {
+  switch (cm) {
+#define NDL_Q(k, pl, hi) case cm_swar(k, pl, hi): return linesq_kernel<cm_swar(k, pl, hi)>;
+    NDL_Q(4, 1, false) NDL_Q(4, 2, false) NDL_Q(4, 3, false)
+    NDL_Q(2, 1, false) NDL_Q(2, 2, false) NDL_Q(2, 3, false)
+    NDL_Q(4, 1, true) NDL_Q(4, 2, true)
+    NDL_Q(2, 1, true) NDL_Q(2, 2, true)
+#undef NDL_Q
+    default: return nullptr;
+  }
+}
+
+static void fill_lines8_params(Lines8Params& lp, const BatchParams& bp, const Lines8Blob& img) {
+  lp.g = bp;
+  lp.image = img.dev;
+  lp.trans_bytes = img.trans_bytes;
+  lp.root_entry = img.root_entry;
+  lp.bwd_root = img.bwd_root;
+  lp.bwd_dead = img.bwd_dead;
+  lp.ua = img.ua;
+  lp.ub = img.ub;
+  lp.xa = img.xa;
+  lp.xb = img.xb;
+  lp.mixed_page = img.mixed_page;
+  lp.replicated = img.replicated;
+  lp.row_bytes = img.row_bytes;
+  lp.char_mode = img.char_mode;
+  lp.has_bwd = img.has_bwd ? 1 : 0;
+  lp.q = img.q;
+}
+
 // Launch the kernels for one batch whose buffers are all on the device.
 static int launch_batch(ndl_pattern* p, const BatchParams& bp, int char_width, uint64_t total_chars, cudaStream_t stream) {
   if (bp.n == 0) return NDL_OK;
   (void)total_chars;
+  const Lines8Blob& qimg = char_width == 1 ? p->q8[bp.mode] : p->q16[bp.mode];
+  if (bp.from == nullptr && qimg.ok && bp.n >= 2 && bp.n < (1ull << 31)) {
+    Lines8Params lp;
+    fill_lines8_params(lp, bp, qimg);
+    const uint64_t per_cta = 32ull * 21;  // lines a CTA's warps take per round
+    const uint64_t want = (bp.n + per_cta - 1) / per_cta;
+    const int blocks = static_cast<int>(want < static_cast<uint64_t>(p->sm_count) ? want : p->sm_count);
+    linesq_kernel_for(qimg.char_mode)<<<blocks, kQThreads, kL8DynSmem, stream>>>(lp);
+    g_launches.fetch_add(1);
+    NDL_CUDA(cudaGetLastError());
+    return NDL_OK;
+  }
   const Lines8Blob& img = char_width == 1 ? p->l8[bp.mode] : p->l16[bp.mode];
   if (bp.from == nullptr && img.ok && bp.n >= 2 && bp.n < (1ull << 31)) {
     Lines8Params lp;
-    lp.g = bp;
-    lp.image = img.dev;
-    lp.trans_bytes = img.trans_bytes;
-    lp.root_entry = img.root_entry;
-    lp.bwd_root = img.bwd_root;
-    lp.bwd_dead = img.bwd_dead;
-    lp.ua = img.ua;
-    lp.ub = img.ub;
-    lp.xa = img.xa;
-    lp.xb = img.xb;
-    lp.mixed_page = img.mixed_page;
-    lp.replicated = img.replicated;
-    lp.row_bytes = img.row_bytes;
-    lp.char_mode = img.char_mode;
-    lp.has_bwd = img.has_bwd ? 1 : 0;
+    fill_lines8_params(lp, bp, img);
     uint64_t max_tiles = (bp.n + 1023) / 1024;  // a CTA's 32 warps take 32 lines each per round
     int blocks = static_cast<int>(max_tiles < static_cast<uint64_t>(p->sm_count) ? max_tiles : p->sm_count);
     lines8_kernel<<<blocks, kL8Threads, kL8DynSmem, stream>>>(lp);
@@ -204,9 +239,131 @@ int ndl_pattern_device(const ndl_pattern* p) { return p ? p->device : -1; }
 // takes.  -1: generic_batch_kernel; otherwise lines8 with char_mode | replicated << 8 | has_bwd << 16 | n_cols << 24.
 int ndl_debug_fast_path(const ndl_pattern* p, int mode, int char_width) {
   if (!p || mode < 0 || mode > 2) return -1;
-  const Lines8Blob& b = char_width == 1 ? p->l8[mode] : p->l16[mode];
+  const Lines8Blob& qb = char_width == 1 ? p->q8[mode] : p->q16[mode];
+  const Lines8Blob& b = qb.ok ? qb : char_width == 1 ? p->l8[mode] : p->l16[mode];
   if (!b.ok) return -1;
   return b.char_mode | (b.replicated << 8) | ((b.has_bwd ? 1 : 0) << 16) | (b.n_cols << 24);
+}
+
+// Test hook (not in include/needle_b200.h; host only, no device needed): builds the SWAR image of
+// (mode, char_width) exactly as ndl_pattern_create does and walks `data` through it on the host with the
+// kernel's own integer arithmetic (packed compares, IDP.4A, entry decoding) as lane `lane`, forwards or -
+// with the BACKWARDS rows - backwards from the end.  Compares the accept flag after every char and the
+// final state with a plain walk of the device table.  Returns the number of differences (0 = identical),
+// -1 when the class map has no SWAR plan, -2 on bad arguments.  info[0..3] = char mode, copies, codes, image bytes.
+int ndl_debug_swar_emulate(const uint8_t* blob, size_t blob_len, int mode, int char_width, int backward, int lane,
+                           const uint8_t* data, uint64_t n_chars, int32_t* info) {
+  if (!blob || mode < 0 || mode > 2 || (char_width != 1 && char_width != 2) || lane < 0 || lane > 31) return -2;
+  CompiledPattern cp;
+  try {
+    cp = deserialize_pattern(blob, blob_len);
+  } catch (const std::exception&) {
+    return -2;
+  }
+  const HostDeviceTable f = build_device_table(cp, mode == NDL_MODE_FIND ? kForwards : mode);
+  const HostDeviceTable bt = build_device_table(cp, kBackwards);
+  const bool want_bwd = mode == NDL_MODE_FIND && cp.reverse_mode == kReverseTable;
+  if (backward && !want_bwd) return -2;
+  std::vector<uint8_t> img;
+  Lines8Blob b;
+  bool ok = want_bwd && linesq_layout(f, &bt, char_width, img, b);
+  if (!ok) {
+    if (backward) return -1;
+    ok = linesq_layout(f, nullptr, char_width, img, b);
+  }
+  if (!ok) return -1;
+  if (info) {
+    info[0] = b.char_mode;
+    info[1] = b.replicated;
+    info[2] = b.n_cols;
+    info[3] = static_cast<int32_t>(img.size());
+  }
+  const int K = cm_k(b.char_mode), P = cm_planes(b.char_mode);
+  const uint32_t state_mask = 0xffffffffu >> K;
+  const uint32_t lane_off = (static_cast<uint32_t>(lane) & b.q.copy_mask) * b.q.copy_bytes;
+  const HostDeviceTable& t = backward ? bt : f;
+  auto slot_at = [&](uint64_t i) -> uint32_t {  // slot value of char i (0 past the end)
+    if (i >= n_chars) return 0;
+    return char_width == 1 ? data[i] : data[2 * i + 1];
+  };
+  auto char_at = [&](uint64_t i) -> uint32_t { return char_width == 1 ? data[i] : (data[2 * i] | data[2 * i + 1] << 8); };
+  auto dp4a = [](uint32_t a, uint32_t w, uint32_t c) {
+    for (int i = 0; i < 4; i++) c += ((a >> (8 * i)) & 0xff) * ((w >> (8 * i)) & 0xff);
+    return c;
+  };
+  auto lds = [&](uint32_t addr) -> uint32_t {
+    uint32_t v = 0;
+    if (addr < kQAbsTrans || addr - kQAbsTrans + 4 > img.size()) return 0xdeadbeefu;
+    std::memcpy(&v, img.data() + (addr - kQAbsTrans), 4);
+    return v;
+  };
+  int diffs = 0;
+  uint32_t e = (backward ? b.bwd_root : b.root_entry) + lane_off;
+  int st = 0;
+  const uint64_t groups = (n_chars + 3) / 4;
+  for (uint64_t gi = 0; gi < groups; gi++) {
+    // word of four slot values in walk order: forwards chars 4g..4g+3 sit in bytes 0..3; backwards the walk
+    // starts at the last char, and the kernel's reverse step reads byte 3 first
+    uint32_t w = 0;
+    uint64_t idx[4];
+    for (int j = 0; j < 4; j++) {
+      idx[j] = backward ? n_chars - 1 - (4 * gi + j) : 4 * gi + j;  // j-th char walked (may wrap past 0: then >= n_chars)
+      const uint32_t sv = idx[j] < n_chars ? slot_at(idx[j]) : 0;
+      w |= sv << (8 * (backward ? 3 - j : j));
+    }
+    const uint32_t w80 = w | 0x80808080u, nm = ~w & 0x80808080u;
+    uint32_t pl[3] = {0, 0, 0};
+    for (int p = 0; p < P; p++) pl[p] = ((w80 - b.q.lo[p]) ^ (w80 - b.q.hi[p])) & nm;
+    uint32_t flags4 = 0;
+    if (K == 4) {
+      uint32_t dp = 0;
+      for (int p = 0; p < P; p++) dp = dp4a(pl[p], b.q.w[p][backward ? 2 : 0], dp);
+      e = lds(dp * b.q.kmul + (e & state_mask));
+      flags4 = e >> 28;
+    } else {
+      uint32_t da = 0, db = 0;
+      for (int p = 0; p < P; p++) {
+        da = dp4a(pl[p], b.q.w[p][backward ? 2 : 0], da);
+        db = dp4a(pl[p], b.q.w[p][backward ? 3 : 1], db);
+      }
+      e = lds(da * b.q.kmul + (e & state_mask));
+      flags4 = (e >> 30) << 2;
+      e = lds(db * b.q.kmul + (e & state_mask));
+      flags4 |= e >> 30;
+    }
+    for (int j = 0; j < 4; j++) {
+      if (idx[j] >= n_chars) break;
+      st = t.trans[static_cast<size_t>(st) * t.n_classes + t.cmap[char_at(idx[j])]];
+      const bool got = (flags4 >> (3 - j)) & 1;
+      if (got != (t.accept[st] != 0)) diffs++;
+    }
+    if (n_chars % 4 == 0 || gi + 1 < groups) {  // whole groups only: the state is comparable
+      const uint32_t row = static_cast<uint32_t>((backward ? f.n_states + 1 : 0) + st);
+      const uint32_t W = 32 / b.replicated;
+      const uint32_t want = kQAbsTrans + (row / W) * 128u + (static_cast<uint32_t>(lane) & b.q.copy_mask) * 4u * W + (row % W) * 4u;
+      if ((e & state_mask) != want) diffs++;
+    }
+  }
+  return diffs;
+}
+
+// Bench / test hook (not in include/needle_b200.h): the name of the kernel a (mode, char_width) batch without
+// `from` offsets is scanned by, for the roofline record.
+const char* ndl_debug_kernel_name(const ndl_pattern* p, int mode, int char_width) {
+  static thread_local std::string name;
+  if (!p || mode < 0 || mode > 2) return "";
+  const Lines8Blob& qb = char_width == 1 ? p->q8[mode] : p->q16[mode];
+  const Lines8Blob& lb = char_width == 1 ? p->l8[mode] : p->l16[mode];
+  if (qb.ok) {
+    name = "linesq_kernel<" + std::to_string(cm_k(qb.char_mode)) + " chars/lookup, " + std::to_string(cm_planes(qb.char_mode)) +
+           " compare planes, " + std::to_string(qb.replicated) + " table copies" + (cm_hi(qb.char_mode) ? ", UTF-16 high byte>" : ">");
+  } else if (lb.ok) {
+    static const char* kModes[] = {"pair table", "UTF-16 high byte", "UTF-16 mixed page", "stride-1 table"};
+    name = std::string("lines8_kernel<") + kModes[lb.char_mode & 3] + ">";
+  } else {
+    name = char_width == 1 ? "generic_batch_kernel<uint8_t>" : "generic_batch_kernel<uint16_t>";
+  }
+  return name.c_str();
 }
 
 int ndl_pattern_create(const uint8_t* blob, size_t blob_len, int device, ndl_pattern** out) {
@@ -267,6 +424,31 @@ int ndl_pattern_create(const uint8_t* blob, size_t blob_len, int device, ndl_pat
         return fail(NDL_ECUDA, "uploading the shared-memory table image failed");
       }
       b.ok = true;
+    }
+  // SWAR images (linesq_kernel), where the class map can be evaluated with packed compares
+  for (int cw = 1; cw <= 2 && ae == cudaSuccess; cw++)
+    for (int mode = 0; mode < 3; mode++) {
+      const HostDeviceTable& fwd_t = p->tables[mode == NDL_MODE_FIND ? kForwards : mode].host;
+      const bool want_bwd = mode == NDL_MODE_FIND && p->cp.reverse_mode == kReverseTable;
+      const HostDeviceTable* bwd_t = want_bwd ? &p->tables[kBackwards].host : nullptr;
+      std::vector<uint8_t> img;
+      Lines8Blob b;
+      bool ok = want_bwd && linesq_layout(fwd_t, bwd_t, cw, img, b);
+      if (!ok) ok = linesq_layout(fwd_t, nullptr, cw, img, b);
+      LinesqKernel kern = ok ? linesq_kernel_for(b.char_mode) : nullptr;
+      if (!kern) continue;
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kL8DynSmem) != cudaSuccess) {
+        cudaGetLastError();
+        continue;
+      }
+      if (cudaMalloc(&b.dev, img.size()) != cudaSuccess ||
+          cudaMemcpy(b.dev, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError();
+        free_pattern(p);
+        return fail(NDL_ECUDA, "uploading the SWAR table image failed");
+      }
+      b.ok = true;
+      (cw == 1 ? p->q8[mode] : p->q16[mode]) = b;
     }
   if (ae != cudaSuccess) cudaGetLastError();  // device cannot give the kernel its shared memory: generic path only
   *out = p;

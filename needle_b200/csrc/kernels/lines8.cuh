@@ -46,6 +46,7 @@
 
 #include "../device_image.h"
 #include "generic.cuh"
+#include "swar_plan.h"
 
 namespace ndl {
 
@@ -83,6 +84,34 @@ constexpr uint32_t kS1UpperLo = kS1AbsTrans + kS1MaxTransBytes;  // 0x28800
 // Any other UTF-16 class map is left to the generic kernel.
 //   kCmBytes1 char_width 1, ONE char per step over the S1 layout (see kS1* above).
 enum { kCmBytes = 0, kCmHi = 1, kCmMixed = 2, kCmBytes1 = 3 };
+// SWAR modes ("Q" layout, linesq_kernel): no class map in shared memory at all.  The class of a char comes
+// from packed compares (swar_plan.h), the automaton is stepped K = 2 or 4 chars per transition lookup, and
+// the column offset of a K-char group is a dot product (IDP.4A) of the compare planes with per-position
+// weights.  Encoded as 16 | (K == 4) << 3 | hi << 2 | planes:
+//   hi = 0  char_width 1, four chars per word
+//   hi = 1  char_width 2 with the class decided by the HIGH byte of a char (as kCmHi): the high bytes of
+//           two words are gathered into one (PRMT) and then classified like bytes
+__host__ __device__ constexpr int cm_swar(int k, int planes, bool hi) { return 16 | (k == 4 ? 8 : 0) | (hi ? 4 : 0) | planes; }
+__host__ __device__ constexpr bool cm_is_swar(int cm) { return cm >= 16; }
+__host__ __device__ constexpr int cm_k(int cm) { return (cm & 8) ? 4 : 2; }
+__host__ __device__ constexpr int cm_planes(int cm) { return cm & 3; }
+__host__ __device__ constexpr bool cm_hi(int cm) { return (cm & 4) != 0; }
+// Q layout: [kQAbsTrans, + trans_bytes) transition table, then 2 KB tile buffers up to the mbarrier.
+constexpr uint32_t kQAbsTrans = 0x800;
+constexpr uint32_t kQMaxTransBytes = 0x22000;  // 139264: leaves 43 tile buffers = 21 warps
+constexpr int kQWarps = 24;
+constexpr int kQThreads = kQWarps * 32;
+
+// What the kernels need of a SwarPlan; a kernel parameter, so every field is a constant-bank operand.
+struct SwarDev {
+  uint32_t lo[3], hi[3];  // range bounds replicated into the four bytes of a word
+  // IDP.4A weights per plane.  K = 4: [0] forward, [2] reverse.  K = 2: [0], [1] forward pairs (bytes 0,1 and
+  // 2,3); [2], [3] reverse pairs (bytes 3,2 and 1,0).  The first char of a group is the most significant digit.
+  uint32_t w[3][4];
+  uint32_t kmul;          // 128-byte lines per table column: entry address = dot product * kmul + row part
+  uint32_t copy_mask;     // R - 1: lane l uses copy l & (R - 1)
+  uint32_t copy_bytes;    // bytes of one copy inside a 128-byte line (4 * 32 / R)
+};
 
 // Device image for one (mode, char width): [cmap 64 KB][trans], plus what the kernel needs to start a walk.
 struct Lines8Blob {
@@ -100,6 +129,7 @@ struct Lines8Blob {
   int n_cols = 0;            // C
   bool has_bwd = false;
   bool ok = false;
+  SwarDev q = {};            // SWAR modes
 };
 
 // Build the shared-memory image for 2-char steps: the forward automaton of the mode and, optionally, the
@@ -251,6 +281,140 @@ inline bool lines8_layout_s1(const HostDeviceTable& f, std::vector<uint8_t>& img
   return true;
 }
 
+// The Q image (SWAR modes): only a transition table.  Entry (row, column) of copy q lives at
+//   column * kmul * 128 + (row / W) * 128 + q * 4W + (row % W) * 4,      W = 32 / R banks per copy
+// so that with R = 32 every lane has a private bank (conflict free) and with fewer copies the 32 / R lanes
+// that share a copy spread over its W banks by row number.  An entry is the absolute shared-memory address
+// of the target row's slot in the same copy, with the accept flags of the K steps in the top K bits
+// (bit 31 = after the first char).  Columns are numbered c1 * n^(K-1) + ... + cK over the n codes of the plan.
+// Preference order = estimated wavefronts per char (lookups per char x expected bank-conflict degree).
+inline bool linesq_layout(const HostDeviceTable& f, const HostDeviceTable* b, int char_width, std::vector<uint8_t>& img,
+                          Lines8Blob& meta) {
+  using Key = std::pair<int, int>;
+  // classes whose table columns are identical (e.g. "in no range" and "above maxChar", both dead) are one class
+  auto canonical = [](const HostDeviceTable& t) {
+    std::vector<int> canon(t.n_classes);
+    for (int k = 0; k < t.n_classes; k++) {
+      canon[k] = k;
+      for (int j = 0; j < k && canon[k] == k; j++) {
+        bool same = true;
+        for (int s = 0; s <= t.n_states && same; s++)
+          same = t.trans[static_cast<size_t>(s) * t.n_classes + k] == t.trans[static_cast<size_t>(s) * t.n_classes + j];
+        if (same) canon[k] = canon[j];
+      }
+    }
+    return canon;
+  };
+  const std::vector<int> canon_f = canonical(f), canon_b = b ? canonical(*b) : std::vector<int>();
+  auto key_of = [&](int c) { return Key{canon_f[f.cmap[c]], b ? canon_b[b->cmap[c]] : 0}; };
+  std::vector<Key> classes;
+  auto id_of = [&](const Key& k) {
+    for (size_t i = 0; i < classes.size(); i++)
+      if (classes[i] == k) return static_cast<int>(i);
+    classes.push_back(k);
+    return static_cast<int>(classes.size() - 1);
+  };
+  int key[256];
+  const bool hi = char_width == 2;
+  if (!hi) {
+    for (int v = 0; v < 256; v++) key[v] = id_of(key_of(v));
+  } else {
+    for (int h = 0; h < 256; h++) {
+      for (int lo = 1; lo < 256; lo++)
+        if (!(key_of(h << 8 | lo) == key_of(h << 8))) return false;  // (includes U+FFFF, whose class is always 0)
+      key[h] = id_of(key_of(h << 8));
+    }
+  }
+  SwarPlan plan;
+  if (!swar_solve(key, 6, plan)) return false;
+  const int n = plan.n_codes;
+  const int rows_f = f.n_states + 1, rows_b = b ? b->n_states + 1 : 0, rows = rows_f + rows_b;
+  struct Cand { int k, r; };
+  static const Cand kCands[] = {{4, 32}, {4, 16}, {2, 32}, {4, 8}, {4, 4}, {2, 16}, {2, 8}};
+  int K = 0, R = 0, W = 0, lines_per_col = 0;
+  uint32_t n_cols = 0;
+  for (const Cand& c : kCands) {
+    long cols = 1;
+    for (int i = 0; i < c.k; i++) cols *= n;
+    int vmax = 0;
+    for (int p = 0; p < plan.planes; p++) vmax = plan.val[p] > vmax ? plan.val[p] : vmax;
+    if (vmax * (cols / n) > 255) continue;  // IDP.4A weights are bytes
+    const int w = 32 / c.r;
+    const long lpc = (rows + w - 1) / w;
+    if (cols * lpc * 128 > static_cast<long>(kQMaxTransBytes)) continue;
+    K = c.k; R = c.r; W = w; lines_per_col = static_cast<int>(lpc); n_cols = static_cast<uint32_t>(cols);
+    break;
+  }
+  if (K == 0) return false;
+  const uint32_t trans_bytes = n_cols * static_cast<uint32_t>(lines_per_col) * 128u;
+  img.assign(trans_bytes, 0);
+  auto slot_off = [&](uint32_t row, uint32_t copy) {  // offset of a row's slot inside a column
+    return (row / W) * 128u + copy * 4u * W + (row % W) * 4u;
+  };
+  auto emit = [&](const HostDeviceTable& t, int row0, bool backward) {
+    const int rows_t = t.n_states + 1;
+    std::vector<int> cls(n);  // table class of every code (unused codes behave like code 0)
+    for (int c = 0; c < n; c++) {
+      const int slot = plan.slot_of_code[c] >= 0 ? plan.slot_of_code[c] : plan.slot_of_code[0] >= 0 ? plan.slot_of_code[0] : 128;
+      cls[c] = t.cmap[hi ? slot << 8 : slot];
+    }
+    (void)backward;
+    for (int s = 0; s < rows_t; s++)
+      for (uint32_t col = 0; col < n_cols; col++) {
+        int st = s;
+        uint32_t flags = 0, rem = col, div = n_cols;
+        for (int i = 0; i < K; i++) {
+          div /= n;
+          const int code = static_cast<int>(rem / div);
+          rem %= div;
+          st = t.trans[static_cast<size_t>(st) * t.n_classes + cls[code]];
+          if (t.accept[st]) flags |= 0x80000000u >> i;
+        }
+        for (int q = 0; q < R; q++) {
+          const uint32_t v = (kQAbsTrans + slot_off(static_cast<uint32_t>(row0 + st), q)) | flags;
+          const uint32_t at = col * static_cast<uint32_t>(lines_per_col) * 128u + slot_off(static_cast<uint32_t>(row0 + s), q);
+          std::memcpy(img.data() + at, &v, 4);
+        }
+      }
+  };
+  emit(f, 0, false);
+  meta = Lines8Blob();
+  meta.has_bwd = b != nullptr;
+  if (b) {
+    emit(*b, rows_f, true);
+    meta.bwd_root = kQAbsTrans + slot_off(static_cast<uint32_t>(rows_f), 0);
+    meta.bwd_dead = kQAbsTrans + slot_off(static_cast<uint32_t>(rows_f + b->n_states), 0);
+  }
+  meta.root_entry = kQAbsTrans;
+  meta.trans_bytes = trans_bytes;
+  meta.replicated = R;
+  meta.n_cols = n;
+  meta.row_bytes = 0;
+  meta.char_mode = cm_swar(K, plan.planes, hi);
+  SwarDev& q = meta.q;
+  for (int p = 0; p < 3; p++) {
+    const bool on = p < plan.planes;
+    q.lo[p] = on ? static_cast<uint32_t>(plan.lo[p]) * 0x01010101u : 0;
+    q.hi[p] = on ? static_cast<uint32_t>(plan.hi[p]) * 0x01010101u : 0;
+    const uint32_t v = on ? static_cast<uint32_t>(plan.val[p]) : 0;
+    const uint32_t un = static_cast<uint32_t>(n);
+    if (K == 4) {
+      q.w[p][0] = v * un * un * un | (v * un * un) << 8 | (v * un) << 16 | v << 24;
+      q.w[p][2] = v | (v * un) << 8 | (v * un * un) << 16 | (v * un * un * un) << 24;
+      q.w[p][1] = q.w[p][3] = 0;
+    } else {
+      q.w[p][0] = v * un | v << 8;
+      q.w[p][1] = (v * un) << 16 | v << 24;
+      q.w[p][2] = v << 16 | (v * un) << 24;
+      q.w[p][3] = v | (v * un) << 8;
+    }
+  }
+  q.kmul = static_cast<uint32_t>(lines_per_col);
+  q.copy_mask = static_cast<uint32_t>(R - 1);
+  q.copy_bytes = 4u * W;
+  return true;
+}
+
 struct Lines8Params {
   BatchParams g;         // buffers, mode, lengths, generic tables (irregular tiles, reverse pass)
   const uint8_t* image;  // [cmap][trans]
@@ -264,6 +428,7 @@ struct Lines8Params {
   uint32_t row_bytes;
   int char_mode;
   int has_bwd;  // BACKWARDS pair table resident: table-driven reverse pass runs on the staged tile
+  SwarDev q;    // SWAR modes
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -320,6 +485,16 @@ struct L8Ctx {
   uint32_t ua, ub;        // kCmMixed: CA / CB value of the common class of all other pages
   uint32_t xa, xb;        // UTF-16 modes: CA / CB value of U+FFFF, whose class never follows its page
   uint32_t row_bytes;     // kCmBytes1
+  uint32_t root;          // entry value of "in the root state" (SWAR modes: this lane's copy)
+  uint32_t bwd_root, bwd_dead;  // the same for the BACKWARDS rows; row of its DEAD state
+};
+
+// How a table entry encodes state and accept flags, per char mode.
+template <int CM>
+struct L8Enc {
+  static constexpr uint32_t kStateMask = CM == kCmBytes1 ? 0x7fffu : cm_is_swar(CM) ? (0xffffffffu >> cm_k(CM)) : kL8FlagMask;
+  // accept flag of the LAST char of a step (kCmBytes1 entries are sign-extended, so bit 30 works there too)
+  static constexpr uint32_t kTailFlag = cm_is_swar(CM) ? (0x80000000u >> (cm_k(CM) - 1)) : 0x40000000u;
 };
 
 // One 2-char step.  KA / KB: byte index (within the 32-bit word) that selects the class-map slot of the
@@ -390,23 +565,92 @@ __device__ __forceinline__ void l8_word_rev(uint32_t w, const L8Ctx& cx, uint32_
 }
 template <int CM>
 struct L8Chars {
-  static constexpr int kBytes = (CM == kCmBytes || CM == kCmBytes1) ? 1 : 2;   // bytes per char
+  static constexpr int kBytes = (CM == kCmBytes || CM == kCmBytes1 || (cm_is_swar(CM) && !cm_hi(CM))) ? 1 : 2;   // bytes per char
   static constexpr int kPerChunk = 16 / kBytes;           // chars (= accept bits) per 16-byte chunk
 };
+
+// SWAR modes: one word = four slot values (bytes, or gathered high bytes).  Packed compares give one plane per
+// range (swar_plan.h), IDP.4A turns the planes into the column offset of the group, one lookup steps K chars.
+template <int CM, bool REV>
+__device__ __forceinline__ void q_word(uint32_t w, const Lines8Params& p, uint32_t& e, uint32_t& mask) {
+  constexpr int P = cm_planes(CM), K = cm_k(CM);
+  constexpr uint32_t kState = L8Enc<CM>::kStateMask;
+  const uint32_t w80 = w | 0x80808080u;
+  const uint32_t nm = ~w & 0x80808080u;
+  uint32_t pl[P];
+#pragma unroll
+  for (int i = 0; i < P; i++) pl[i] = ((w80 - p.q.lo[i]) ^ (w80 - p.q.hi[i])) & nm;
+  if (K == 4) {
+    uint32_t dp = 0;
+#pragma unroll
+    for (int i = 0; i < P; i++) dp = __dp4a(pl[i], p.q.w[i][REV ? 2 : 0], dp);
+    e = lds_tab(dp * p.q.kmul + (e & kState));
+    mask = __funnelshift_l(e, mask, 4);
+  } else {
+    uint32_t da = 0, db = 0;
+#pragma unroll
+    for (int i = 0; i < P; i++) {
+      da = __dp4a(pl[i], p.q.w[i][REV ? 2 : 0], da);
+      db = __dp4a(pl[i], p.q.w[i][REV ? 3 : 1], db);
+    }
+    e = lds_tab(da * p.q.kmul + (e & kState));
+    mask = __funnelshift_l(e, mask, 2);
+    e = lds_tab(db * p.q.kmul + (e & kState));
+    mask = __funnelshift_l(e, mask, 2);
+  }
+}
+
+// All chars of one 16-byte chunk, forwards / backwards.  Afterwards the low L8Chars<CM>::kPerChunk bits of
+// `mask` are the accept flags of these chars, bit 0 = the char walked last.
+template <int CM>
+__device__ __forceinline__ void l8_chunk(const uint4& w, const Lines8Params& p, const L8Ctx& cx, uint32_t& e, uint32_t& mask) {
+  if constexpr (cm_is_swar(CM)) {
+    if constexpr (cm_hi(CM)) {
+      q_word<CM, false>(__byte_perm(w.x, w.y, 0x7531), p, e, mask);
+      q_word<CM, false>(__byte_perm(w.z, w.w, 0x7531), p, e, mask);
+    } else {
+      q_word<CM, false>(w.x, p, e, mask);
+      q_word<CM, false>(w.y, p, e, mask);
+      q_word<CM, false>(w.z, p, e, mask);
+      q_word<CM, false>(w.w, p, e, mask);
+    }
+  } else {
+    l8_word<CM>(w.x, cx, e, mask);
+    l8_word<CM>(w.y, cx, e, mask);
+    l8_word<CM>(w.z, cx, e, mask);
+    l8_word<CM>(w.w, cx, e, mask);
+  }
+}
+template <int CM>
+__device__ __forceinline__ void l8_chunk_rev(const uint4& w, const Lines8Params& p, const L8Ctx& cx, uint32_t& e, uint32_t& mask) {
+  if constexpr (cm_is_swar(CM)) {
+    if constexpr (cm_hi(CM)) {
+      q_word<CM, true>(__byte_perm(w.z, w.w, 0x7531), p, e, mask);
+      q_word<CM, true>(__byte_perm(w.x, w.y, 0x7531), p, e, mask);
+    } else {
+      q_word<CM, true>(w.w, p, e, mask);
+      q_word<CM, true>(w.z, p, e, mask);
+      q_word<CM, true>(w.y, p, e, mask);
+      q_word<CM, true>(w.x, p, e, mask);
+    }
+  } else {
+    l8_word_rev<CM>(w.w, cx, e, mask);
+    l8_word_rev<CM>(w.z, cx, e, mask);
+    l8_word_rev<CM>(w.y, cx, e, mask);
+    l8_word_rev<CM>(w.x, cx, e, mask);
+  }
+}
 
 // Realign 16 bytes that start `sh` bytes into chunk x (continuing in chunk y) into four words.
 struct L8Align {
   bool q1, q2;
   uint32_t r8;
   __device__ __forceinline__ explicit L8Align(uint32_t sh) : q1((sh & 4u) != 0), q2((sh & 8u) != 0), r8((sh & 3u) * 8u) {}
-  __device__ __forceinline__ void apply(const uint4& x, const uint4& y, uint32_t (&w)[4]) const {
+  __device__ __forceinline__ uint4 apply(const uint4& x, const uint4& y) const {
     const uint32_t a0 = q2 ? x.z : x.x, a1 = q2 ? x.w : x.y, a2 = q2 ? y.x : x.z, a3 = q2 ? y.y : x.w;
     const uint32_t a4 = q2 ? y.z : y.x, a5 = q2 ? y.w : y.y;
     const uint32_t w0 = q1 ? a1 : a0, w1 = q1 ? a2 : a1, w2 = q1 ? a3 : a2, w3 = q1 ? a4 : a3, w4 = q1 ? a5 : a4;
-    w[0] = __funnelshift_r(w0, w1, r8);
-    w[1] = __funnelshift_r(w1, w2, r8);
-    w[2] = __funnelshift_r(w2, w3, r8);
-    w[3] = __funnelshift_r(w3, w4, r8);
+    return make_uint4(__funnelshift_r(w0, w1, r8), __funnelshift_r(w1, w2, r8), __funnelshift_r(w2, w3, r8), __funnelshift_r(w3, w4, r8));
   }
 };
 
@@ -419,24 +663,20 @@ __device__ __forceinline__ int32_t l8_reverse(const Lines8Params& p, ChunkAddr c
                                               bool bwd_root_accepting) {
   constexpr int kPer = L8Chars<CM>::kPerChunk;
   int32_t st = bwd_root_accepting ? 0 : 0x7fffffff;
-  uint32_t e = p.bwd_root;
+  uint32_t e = cx.bwd_root;
   for (int32_t rem = last; rem > 0; rem -= kPer) {
     const uint32_t h = ps + static_cast<uint32_t>(rem) * L8Chars<CM>::kBytes;  // window = bytes [h - 16, h)
     const uint32_t q = h >> 4;
     const uint4 y = lds_data16(chunk_addr(q));
     const uint4 x = lds_data16(chunk_addr(q > 0 ? q - 1 : 0));
-    uint32_t w[4];
-    L8Align(h & 15u).apply(x, y, w);
+    const uint4 w = L8Align(h & 15u).apply(x, y);
     uint32_t mask = 0;
-    l8_word_rev<CM>(w[3], cx, e, mask);
-    l8_word_rev<CM>(w[2], cx, e, mask);
-    l8_word_rev<CM>(w[1], cx, e, mask);
-    l8_word_rev<CM>(w[0], cx, e, mask);
+    l8_chunk_rev<CM>(w, p, cx, e, mask);
     const int32_t valid = rem < kPer ? rem : kPer;
     mask >>= (kPer - valid);  // drop the steps taken before the start of the line
     const int32_t cand = rem - valid + (__ffs(mask) - 1);
     st = mask ? cand : st;
-    if ((e & kL8FlagMask) == p.bwd_dead) break;
+    if ((e & L8Enc<CM>::kStateMask) == cx.bwd_dead) break;
   }
   return st;
 }
@@ -577,16 +817,13 @@ __device__ __forceinline__ void l8_run(const Lines8Params& p, const L8Ctx& cx, c
     const uint32_t i = t * G::kTileLines + lane;
     if (regular) {
       if (active) {
-        uint32_t e = p.root_entry;
+        uint32_t e = cx.root;
         int32_t last = g.fwd.root_accepting ? 0 : -1;
         uint32_t mask = 0;
 #pragma unroll
         for (uint32_t c = 0; c < G::kCpl; c++) {
           const uint4 w = lds_data16(cur + (l8_slot(lane, c, LOG2CPL) << 4));
-          l8_word<CM>(w.x, cx, e, mask);
-          l8_word<CM>(w.y, cx, e, mask);
-          l8_word<CM>(w.z, cx, e, mask);
-          l8_word<CM>(w.w, cx, e, mask);
+          l8_chunk<CM>(w, p, cx, e, mask);
           constexpr uint32_t kFlush = 32 / kPer;  // chunks whose accept bits fit in the 32-bit mask
           if ((c % kFlush) == kFlush - 1 || c + 1 == G::kCpl) {  // bit 0 = the most recent char
             const int32_t cand = static_cast<int32_t>((c + 1) * kPer + 1) - __ffs(mask);
@@ -594,7 +831,7 @@ __device__ __forceinline__ void l8_run(const Lines8Params& p, const L8Ctx& cx, c
             mask = 0;
           }
         }
-        l8_finish<CM, CharT>(p, cx, i, kLenChars, last, (e & 0x40000000u) != 0, 0u,
+        l8_finish<CM, CharT>(p, cx, i, kLenChars, last, (e & L8Enc<CM>::kTailFlag) != 0, 0u,
                              [&](uint32_t ch) { return cur + (l8_slot(lane, ch & (G::kCpl - 1), LOG2CPL) << 4); });
       }
     } else if (active) {
@@ -692,19 +929,15 @@ __device__ __forceinline__ void l8_run_ragged(const Lines8Params& p, const L8Ctx
       const uint32_t len = pl.len;
       const L8Align al(pl.start & 15u);
       const uint32_t c0 = pl.start >> 4;
-      uint32_t e = p.root_entry;
+      uint32_t e = cx.root;
       int32_t last = g.fwd.root_accepting ? 0 : -1;
       uint32_t tail_bit = g.fwd.root_accepting ? 1u : 0u;  // accept flag exactly at the end of the line (matches())
       uint4 x = lds_data16(cur + l8_rslot(c0));
       for (uint32_t pos = 0; pos < len; pos += kPer) {
         const uint4 y = lds_data16(cur + l8_rslot(c0 + (pos / kPer) + 1));
-        uint32_t w[4];
-        al.apply(x, y, w);
+        const uint4 w = al.apply(x, y);
         uint32_t mask = 0;
-        l8_word<CM>(w[0], cx, e, mask);
-        l8_word<CM>(w[1], cx, e, mask);
-        l8_word<CM>(w[2], cx, e, mask);
-        l8_word<CM>(w[3], cx, e, mask);
+        l8_chunk<CM>(w, p, cx, e, mask);
         const uint32_t valid = min(kPer, len - pos);
         mask >>= (kPer - valid);  // drop the accept bits of chars past the end of the line
         const int32_t cand = static_cast<int32_t>(pos + valid + 1) - __ffs(mask);
@@ -821,10 +1054,69 @@ __global__ void __launch_bounds__(kL8Threads, 1) lines8_kernel(const Lines8Param
   cx.xa = p.xa;
   cx.xb = p.xb + (p.replicated == 32 ? lane * 4 : 0);
   cx.row_bytes = p.row_bytes;
+  cx.root = p.root_entry;
+  cx.bwd_root = p.bwd_root;
+  cx.bwd_dead = p.bwd_dead;
   if (p.char_mode == kCmBytes1) l8_dispatch<kCmBytes1>(p, cx, log2cpl, buf0, buf1, lane, warp_global, n_warps);
   else if (p.char_mode == kCmBytes) l8_dispatch<kCmBytes>(p, cx, log2cpl, buf0, buf1, lane, warp_global, n_warps);
   else if (p.char_mode == kCmHi) l8_dispatch<kCmHi>(p, cx, log2cpl, buf0, buf1, lane, warp_global, n_warps);
   else l8_dispatch<kCmMixed>(p, cx, log2cpl, buf0, buf1, lane, warp_global, n_warps);
+}
+
+// ---------------------------------------------------------------------------------------------
+// linesq_kernel: the SWAR modes.  Same tiles, same walks (l8_run / l8_run_ragged), other table image:
+// [kQAbsTrans, +trans_bytes) transition table, brought in by TMA bulk copies, then 2 KB tile buffers.
+// One instantiation per char mode; 24 warps (the table leaves room for 21-22 pairs of tile buffers).
+// ---------------------------------------------------------------------------------------------
+template <int CM>
+__global__ void __launch_bounds__(kQThreads, 1) linesq_kernel(const Lines8Params p) {
+  const uint32_t tid = threadIdx.x;
+  const uint32_t lane = tid & 31, warp = tid >> 5;
+  const BatchParams& g = p.g;
+  using CharT = typename std::conditional<L8Chars<CM>::kBytes == 1, uint8_t, uint16_t>::type;
+
+  extern __shared__ __align__(128) uint8_t l8_dyn_smem[];
+  const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(l8_dyn_smem));
+  const bool layout_ok = base <= kQAbsTrans;
+  const uint32_t tiles_lo = (kQAbsTrans + p.trans_bytes + 127u) & ~127u;
+  const uint32_t slots = (kL8AbsBar - tiles_lo) / kL8WarpBuf;
+  const uint32_t usable_warps = min(static_cast<uint32_t>(kQWarps), slots / 2);
+  const uint32_t buf0 = tiles_lo + 2 * warp * kL8WarpBuf, buf1 = buf0 + kL8WarpBuf;
+
+  if (tid == 0) {
+    mbar_init(kL8AbsBar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0 && layout_ok) {
+    mbar_expect_tx(kL8AbsBar, p.trans_bytes);
+    for (uint32_t off = 0; off < p.trans_bytes; off += 0x8000u)
+      tma_bulk_g2s(kQAbsTrans + off, p.image + off, min(0x8000u, p.trans_bytes - off), kL8AbsBar);
+  }
+  const uint64_t l_chars = g.offsets[1] - g.offsets[0];
+  const uint64_t L64 = l_chars * L8Chars<CM>::kBytes;
+  int log2cpl = -1;
+  if (L64 >= 16 && L64 <= 256 && (L64 & (L64 - 1)) == 0) log2cpl = 31 - __clz(static_cast<uint32_t>(L64)) - 4;
+  if (log2cpl >= 0) {
+    const uint32_t probe = static_cast<uint32_t>(min(static_cast<uint64_t>(lane) + 1, g.n - 1));
+    const bool same = g.offsets[probe + 1] - g.offsets[probe] == l_chars;
+    if (!__all_sync(0xffffffffu, same)) log2cpl = -1;
+  }
+  if (!layout_ok) {  // unexpected shared-memory base: generic walk, one line per thread
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * kQThreads + tid; i < g.n; i += static_cast<uint64_t>(gridDim.x) * kQThreads)
+      l8_slow_line<CharT>(g, i);
+    return;
+  }
+  mbar_wait(kL8AbsBar, 0);  // table image has landed
+  if (warp >= usable_warps) return;
+  const uint32_t lane_off = (lane & p.q.copy_mask) * p.q.copy_bytes;
+  L8Ctx cx;
+  cx.sel_a = cx.sel_b = cx.page1 = cx.page3 = cx.ua = cx.ub = cx.xa = cx.xb = cx.row_bytes = 0;
+  cx.root = p.root_entry + lane_off;
+  cx.bwd_root = p.bwd_root + lane_off;
+  cx.bwd_dead = p.bwd_dead + lane_off;
+  l8_dispatch<CM>(p, cx, log2cpl, buf0, buf1, lane, blockIdx.x * usable_warps + warp, gridDim.x * usable_warps);
 }
 
 }  // namespace ndl

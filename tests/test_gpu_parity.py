@@ -311,18 +311,66 @@ def fast_path(pat, mode, cw):
 
 
 def test_expected_kernels_are_selected():
-    """Guards against silently falling back to the generic kernel on the BASELINE configs."""
+    """Guards against silently falling back to a slower kernel on the BASELINE configs.  char_mode >= 16 are the
+    SWAR modes of linesq_kernel: 16 | (K == 4) << 3 | high-byte << 2 | planes."""
     fp = fast_path(pair(workloads.REGEX["c2"])[0], 2, 1)
-    assert fp == {"char_mode": 0, "replicated": 32, "has_bwd": 0, "n_cols": 3}
+    assert fp == {"char_mode": 16 | 8 | 2, "replicated": 32, "has_bwd": 0, "n_cols": 3}  # 4 chars per lookup, 2 compare planes
     fp = fast_path(pair(workloads.REGEX["c3"])[0], 2, 1)
-    assert fp["char_mode"] == 0 and fp["replicated"] == 32 and fp["has_bwd"] == 1
+    assert fp["char_mode"] == 0 and fp["replicated"] == 32 and fp["has_bwd"] == 1  # 15 class changes: class map in shared memory
     fp = fast_path(pair(workloads.REGEX["c4"])[0], 2, 1)
-    assert fp["char_mode"] == 3 and fp["replicated"] == 32  # 258 rows: stride-1 16-bit table, bank replicated
+    assert fp == {"char_mode": 16 | 2, "replicated": 8, "has_bwd": 0, "n_cols": 4}  # 258 rows: 2 chars per lookup, 8 copies
     fp = fast_path(pair("a[ab]{8}c|b[ab]{6}d")[0], 2, 1)
     assert fp is None or fp["replicated"] in (1, 32)
     fp = fast_path(pair(workloads.REGEX["c5"])[0], 2, 2)
-    assert fp["char_mode"] == 1 and fp["replicated"] == 32 and fp["has_bwd"] == 1  # class from the high byte
+    assert fp == {"char_mode": 16 | 8 | 4 | 1, "replicated": 32, "has_bwd": 1, "n_cols": 2}  # class from the high byte, 1 plane
     fp = fast_path(pair(workloads.REGEX["c2"])[0], 2, 2)
     assert fp["char_mode"] == 2  # ASCII pattern over UTF-16: one mixed page
     assert fast_path(pair("[a-bα-ω]+")[0], 2, 2) is None  # two mixed pages: generic kernel
     assert fast_path(pair("Holmes.{1,10}Watson|Watson.{1,10}Holmes")[0], 2, 1) is None  # 309 states x 12 classes
+
+
+SWAR_CASES = [
+    (workloads.REGEX["c2"], b"0123456789--- /:,."),
+    (workloads.REGEX["c4"], b"aaabbbc`d"),
+    (r"[0-9]+", b"0123456789/: "),
+    (r"[^a]+b", b"ab`c\x7f\x80"),
+    (r"[a-c]z|[b-d]z", b"abcdz`ey"),
+    (r"\d+-\d+", b"0123456789-,."),
+    ("x[\x01-\x1f]y", b"xy\x00\x1f\x20\x01"),
+    ("[\x7f]+a", b"a\x7f\x7e\x80\xff"),
+    (r"(ab|a|b-)+", b"ab-,.`c"),
+    (r"a+b+", b"ab`c"),
+]
+
+
+@pytest.mark.parametrize("regex,hot", SWAR_CASES, ids=[c[0][:16] for c in SWAR_CASES])
+@pytest.mark.parametrize("line_len", [64, 16, 256, 40, 0])
+def test_swar_modes_all_byte_values(regex, hot, line_len):
+    """linesq_kernel (packed-compare classifier): every byte value, around every range bound, fixed / ragged."""
+    rng = np.random.default_rng(line_len + len(regex))
+    n = 4000
+    if line_len:
+        lens = np.full(n, line_len)
+    else:
+        lens = rng.integers(0, 150, size=n)
+    offsets = np.zeros(n + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum(lens)
+    total = int(offsets[-1])
+    data = rng.integers(0, 256, size=total, dtype=np.uint8)
+    h = np.frombuffer(hot, dtype=np.uint8)
+    pick = rng.random(total) < 0.75
+    data[pick] = h[rng.integers(0, len(h), size=int(pick.sum()))]
+    assert fast_path(pair(regex)[0], 2, 1)["char_mode"] >= 16
+    assert_batch_equal(regex, 0, data, offsets)
+
+
+def test_swar_utf16_all_high_bytes():
+    rng = np.random.default_rng(12)
+    for line_chars in (32, 8, 128, 19):
+        n = 5000
+        chars = rng.integers(0, 0x10000, size=n * line_chars).astype(np.uint16)
+        hotm = rng.random(len(chars)) < 0.6
+        chars[hotm] = rng.integers(0x5F0, 0x710, size=int(hotm.sum()))
+        chars[::101] = 0xFFFF
+        offsets = np.arange(n + 1, dtype=np.uint64) * np.uint64(line_chars)
+        assert_batch_equal(workloads.REGEX["c5"], 0, chars.view(np.uint8), offsets, cw=2)
