@@ -155,6 +155,9 @@ static LinesqKernel linesq_kernel_for(int cm) {
     NDL_Q(4, 1, true) NDL_Q(4, 2, true)
     NDL_Q(2, 1, true) NDL_Q(2, 2, true)
 #undef NDL_Q
+#define NDL_Q16(pl) case cm_swar(2, pl, false, true): return linesq_kernel<cm_swar(2, pl, false, true)>;
+    NDL_Q16(1) NDL_Q16(2) NDL_Q16(3)
+#undef NDL_Q16
     default: return nullptr;
   }
 }
@@ -279,7 +282,8 @@ int ndl_debug_swar_emulate(const uint8_t* blob, size_t blob_len, int mode, int c
     info[3] = static_cast<int32_t>(img.size());
   }
   const int K = cm_k(b.char_mode), P = cm_planes(b.char_mode);
-  const uint32_t state_mask = 0xffffffffu >> K;
+  const bool u16 = cm_u16(b.char_mode);
+  const uint32_t state_mask = u16 ? 0x3fffu : 0xffffffffu >> K;
   const uint32_t lane_off = (static_cast<uint32_t>(lane) & b.q.copy_mask) * b.q.copy_bytes;
   const HostDeviceTable& t = backward ? bt : f;
   auto slot_at = [&](uint64_t i) -> uint32_t {  // slot value of char i (0 past the end)
@@ -294,8 +298,8 @@ int ndl_debug_swar_emulate(const uint8_t* blob, size_t blob_len, int mode, int c
   auto lds = [&](uint32_t addr) -> uint32_t {
     uint32_t v = 0;
     if (addr < kQAbsTrans || addr - kQAbsTrans + 4 > img.size()) return 0xdeadbeefu;
-    std::memcpy(&v, img.data() + (addr - kQAbsTrans), 4);
-    return v;
+    std::memcpy(&v, img.data() + (addr - kQAbsTrans), u16 ? 2 : 4);
+    return u16 ? v << 16 | v : v;  // 16-bit entry: flags seen in the top bits, row address in the low 14
   };
   int diffs = 0;
   uint32_t e = (backward ? b.bwd_root : b.root_entry) + lane_off;
@@ -339,8 +343,8 @@ int ndl_debug_swar_emulate(const uint8_t* blob, size_t blob_len, int mode, int c
     }
     if (n_chars % 4 == 0 || gi + 1 < groups) {  // whole groups only: the state is comparable
       const uint32_t row = static_cast<uint32_t>((backward ? f.n_states + 1 : 0) + st);
-      const uint32_t W = 32 / b.replicated;
-      const uint32_t want = kQAbsTrans + (row / W) * 128u + (static_cast<uint32_t>(lane) & b.q.copy_mask) * 4u * W + (row % W) * 4u;
+      const uint32_t EB = u16 ? 2 : 4, W = 128 / EB / b.replicated;
+      const uint32_t want = kQAbsTrans + (row / W) * 128u + (static_cast<uint32_t>(lane) & b.q.copy_mask) * EB * W + (row % W) * EB;
       if ((e & state_mask) != want) diffs++;
     }
   }
@@ -356,7 +360,7 @@ const char* ndl_debug_kernel_name(const ndl_pattern* p, int mode, int char_width
   const Lines8Blob& lb = char_width == 1 ? p->l8[mode] : p->l16[mode];
   if (qb.ok) {
     name = "linesq_kernel<" + std::to_string(cm_k(qb.char_mode)) + " chars/lookup, " + std::to_string(cm_planes(qb.char_mode)) +
-           " compare planes, " + std::to_string(qb.replicated) + " table copies" + (cm_hi(qb.char_mode) ? ", UTF-16 high byte>" : ">");
+           " compare planes, " + std::to_string(qb.replicated) + (cm_u16(qb.char_mode) ? " table copies of 16-bit entries" : " table copies") + (cm_hi(qb.char_mode) ? ", UTF-16 high byte>" : ">");
   } else if (lb.ok) {
     static const char* kModes[] = {"pair table", "UTF-16 high byte", "UTF-16 mixed page", "stride-1 table"};
     name = std::string("lines8_kernel<") + kModes[lb.char_mode & 3] + ">";

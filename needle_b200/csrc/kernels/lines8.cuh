@@ -87,11 +87,15 @@ enum { kCmBytes = 0, kCmHi = 1, kCmMixed = 2, kCmBytes1 = 3 };
 // SWAR modes ("Q" layout, linesq_kernel): no class map in shared memory at all.  The class of a char comes
 // from packed compares (swar_plan.h), the automaton is stepped K = 2 or 4 chars per transition lookup, and
 // the column offset of a K-char group is a dot product (IDP.4A) of the compare planes with per-position
-// weights.  Encoded as 16 | (K == 4) << 3 | hi << 2 | planes:
+// weights.  Encoded as 16 | u16 << 5 | (K == 4) << 3 | hi << 2 | planes:
+//   u16 = 1 16-bit table entries (K = 2 only): twice the copies in the same space, see linesq_layout
 //   hi = 0  char_width 1, four chars per word
 //   hi = 1  char_width 2 with the class decided by the HIGH byte of a char (as kCmHi): the high bytes of
 //           two words are gathered into one (PRMT) and then classified like bytes
-__host__ __device__ constexpr int cm_swar(int k, int planes, bool hi) { return 16 | (k == 4 ? 8 : 0) | (hi ? 4 : 0) | planes; }
+__host__ __device__ constexpr int cm_swar(int k, int planes, bool hi, bool u16 = false) {
+  return 16 | (u16 ? 32 : 0) | (k == 4 ? 8 : 0) | (hi ? 4 : 0) | planes;
+}
+__host__ __device__ constexpr bool cm_u16(int cm) { return cm >= 16 && (cm & 32) != 0; }
 __host__ __device__ constexpr bool cm_is_swar(int cm) { return cm >= 16; }
 __host__ __device__ constexpr int cm_k(int cm) { return (cm & 8) ? 4 : 2; }
 __host__ __device__ constexpr int cm_planes(int cm) { return cm & 3; }
@@ -99,7 +103,10 @@ __host__ __device__ constexpr bool cm_hi(int cm) { return (cm & 4) != 0; }
 // Q layout: [kQAbsTrans, + trans_bytes) transition table, then 2 KB tile buffers up to the mbarrier.
 constexpr uint32_t kQAbsTrans = 0x800;
 constexpr uint32_t kQMaxTransBytes = 0x22000;  // 139264: leaves 43 tile buffers = 21 warps
-constexpr int kQWarps = 24;
+#ifndef NDL_Q_WARPS
+#define NDL_Q_WARPS 20
+#endif
+constexpr int kQWarps = NDL_Q_WARPS;
 constexpr int kQThreads = kQWarps * 32;
 
 // What the kernels need of a SwarPlan; a kernel parameter, so every field is a constant-bank operand.
@@ -283,6 +290,7 @@ inline bool lines8_layout_s1(const HostDeviceTable& f, std::vector<uint8_t>& img
 
 // The Q image (SWAR modes): only a transition table.  Entry (row, column) of copy q lives at
 //   column * kmul * 128 + (row / W) * 128 + q * 4W + (row % W) * 4,      W = 32 / R banks per copy
+// (16-bit entries: 2 instead of 4 bytes each, W = 64 / R entries per copy and line)
 // so that with R = 32 every lane has a private bank (conflict free) and with fewer copies the 32 / R lanes
 // that share a copy spread over its W banks by row number.  An entry is the absolute shared-memory address
 // of the target row's slot in the same copy, with the accept flags of the K steps in the top K bits
@@ -329,9 +337,14 @@ inline bool linesq_layout(const HostDeviceTable& f, const HostDeviceTable* b, in
   if (!swar_solve(key, 6, plan)) return false;
   const int n = plan.n_codes;
   const int rows_f = f.n_states + 1, rows_b = b ? b->n_states + 1 : 0, rows = rows_f + rows_b;
-  struct Cand { int k, r; };
-  static const Cand kCands[] = {{4, 32}, {4, 16}, {2, 32}, {4, 8}, {4, 4}, {2, 16}, {2, 8}};
-  int K = 0, R = 0, W = 0, lines_per_col = 0;
+  // candidates in order of estimated shared-memory wavefronts per char = (expected conflict degree of one
+  // lookup: 1 with 32 copies, about 2 with 16, about 3 with 8, measured) / K
+  struct Cand { int k, r, bytes; };
+  // 16-bit entries: (2 chars, 16 copies) takes the space of (2 chars, 8 copies of 32-bit entries) and measured the
+  // same speed on the 258-row DFA of BASELINE config 4 (1.3 instead of 1.8 wavefronts per char, but 3 % more
+  // instructions in an issue-bound loop), so 16-bit entries are only used to fit automata of twice the size.
+  static const Cand kCands[] = {{4, 32, 4}, {2, 32, 4}, {4, 16, 4}, {4, 8, 4}, {2, 16, 4}, {2, 8, 4}, {2, 8, 2}};
+  int K = 0, R = 0, W = 0, EB = 4, lines_per_col = 0;
   uint32_t n_cols = 0;
   for (const Cand& c : kCands) {
     long cols = 1;
@@ -339,17 +352,18 @@ inline bool linesq_layout(const HostDeviceTable& f, const HostDeviceTable* b, in
     int vmax = 0;
     for (int p = 0; p < plan.planes; p++) vmax = plan.val[p] > vmax ? plan.val[p] : vmax;
     if (vmax * (cols / n) > 255) continue;  // IDP.4A weights are bytes
-    const int w = 32 / c.r;
+    const int w = 128 / c.bytes / c.r;      // entries of one copy per 128-byte line
     const long lpc = (rows + w - 1) / w;
     if (cols * lpc * 128 > static_cast<long>(kQMaxTransBytes)) continue;
-    K = c.k; R = c.r; W = w; lines_per_col = static_cast<int>(lpc); n_cols = static_cast<uint32_t>(cols);
+    if (c.bytes == 2 && kQAbsTrans + lpc * 128 > 0x4000) continue;  // a 16-bit entry holds a 14-bit row address
+    K = c.k; R = c.r; W = w; EB = c.bytes; lines_per_col = static_cast<int>(lpc); n_cols = static_cast<uint32_t>(cols);
     break;
   }
   if (K == 0) return false;
   const uint32_t trans_bytes = n_cols * static_cast<uint32_t>(lines_per_col) * 128u;
   img.assign(trans_bytes, 0);
   auto slot_off = [&](uint32_t row, uint32_t copy) {  // offset of a row's slot inside a column
-    return (row / W) * 128u + copy * 4u * W + (row % W) * 4u;
+    return (row / W) * 128u + copy * static_cast<uint32_t>(EB * W) + (row % W) * static_cast<uint32_t>(EB);
   };
   auto emit = [&](const HostDeviceTable& t, int row0, bool backward) {
     const int rows_t = t.n_states + 1;
@@ -371,9 +385,15 @@ inline bool linesq_layout(const HostDeviceTable& f, const HostDeviceTable* b, in
           if (t.accept[st]) flags |= 0x80000000u >> i;
         }
         for (int q = 0; q < R; q++) {
-          const uint32_t v = (kQAbsTrans + slot_off(static_cast<uint32_t>(row0 + st), q)) | flags;
+          const uint32_t target = kQAbsTrans + slot_off(static_cast<uint32_t>(row0 + st), q);
           const uint32_t at = col * static_cast<uint32_t>(lines_per_col) * 128u + slot_off(static_cast<uint32_t>(row0 + s), q);
-          std::memcpy(img.data() + at, &v, 4);
+          if (EB == 4) {
+            const uint32_t v = target | flags;
+            std::memcpy(img.data() + at, &v, 4);
+          } else {
+            const uint16_t v = static_cast<uint16_t>(target | flags >> 16);
+            std::memcpy(img.data() + at, &v, 2);
+          }
         }
       }
   };
@@ -390,7 +410,7 @@ inline bool linesq_layout(const HostDeviceTable& f, const HostDeviceTable* b, in
   meta.replicated = R;
   meta.n_cols = n;
   meta.row_bytes = 0;
-  meta.char_mode = cm_swar(K, plan.planes, hi);
+  meta.char_mode = cm_swar(K, plan.planes, hi, EB == 2);
   SwarDev& q = meta.q;
   for (int p = 0; p < 3; p++) {
     const bool on = p < plan.planes;
@@ -411,7 +431,7 @@ inline bool linesq_layout(const HostDeviceTable& f, const HostDeviceTable* b, in
   }
   q.kmul = static_cast<uint32_t>(lines_per_col);
   q.copy_mask = static_cast<uint32_t>(R - 1);
-  q.copy_bytes = 4u * W;
+  q.copy_bytes = static_cast<uint32_t>(EB * W);
   return true;
 }
 
@@ -492,9 +512,9 @@ struct L8Ctx {
 // How a table entry encodes state and accept flags, per char mode.
 template <int CM>
 struct L8Enc {
-  static constexpr uint32_t kStateMask = CM == kCmBytes1 ? 0x7fffu : cm_is_swar(CM) ? (0xffffffffu >> cm_k(CM)) : kL8FlagMask;
+  static constexpr uint32_t kStateMask = CM == kCmBytes1 ? 0x7fffu : cm_u16(CM) ? 0x3fffu : cm_is_swar(CM) ? (0xffffffffu >> cm_k(CM)) : kL8FlagMask;
   // accept flag of the LAST char of a step (kCmBytes1 entries are sign-extended, so bit 30 works there too)
-  static constexpr uint32_t kTailFlag = cm_is_swar(CM) ? (0x80000000u >> (cm_k(CM) - 1)) : 0x40000000u;
+  static constexpr uint32_t kTailFlag = cm_u16(CM) ? 0x4000u : cm_is_swar(CM) ? (0x80000000u >> (cm_k(CM) - 1)) : 0x40000000u;
 };
 
 // One 2-char step.  KA / KB: byte index (within the 32-bit word) that selects the class-map slot of the
@@ -571,12 +591,19 @@ struct L8Chars {
 
 // SWAR modes: one word = four slot values (bytes, or gathered high bytes).  Packed compares give one plane per
 // range (swar_plan.h), IDP.4A turns the planes into the column offset of the group, one lookup steps K chars.
+__device__ __forceinline__ uint32_t lds_tab_u16(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
 template <int CM, bool REV>
 __device__ __forceinline__ void q_word(uint32_t w, const Lines8Params& p, uint32_t& e, uint32_t& mask) {
   constexpr int P = cm_planes(CM), K = cm_k(CM);
   constexpr uint32_t kState = L8Enc<CM>::kStateMask;
   const uint32_t w80 = w | 0x80808080u;
-  const uint32_t nm = ~w & 0x80808080u;
+  uint32_t nm;  // kept out of the compiler's hands: one LOP3 here, then one per plane
+  asm("lop3.b32 %0, %1, 0x80808080, 0, 0x0c;" : "=r"(nm) : "r"(w));  // ~w & 0x80808080 (LUT: ~a & b)
   uint32_t pl[P];
 #pragma unroll
   for (int i = 0; i < P; i++) pl[i] = ((w80 - p.q.lo[i]) ^ (w80 - p.q.hi[i])) & nm;
@@ -593,10 +620,17 @@ __device__ __forceinline__ void q_word(uint32_t w, const Lines8Params& p, uint32
       da = __dp4a(pl[i], p.q.w[i][REV ? 2 : 0], da);
       db = __dp4a(pl[i], p.q.w[i][REV ? 3 : 1], db);
     }
-    e = lds_tab(da * p.q.kmul + (e & kState));
-    mask = __funnelshift_l(e, mask, 2);
-    e = lds_tab(db * p.q.kmul + (e & kState));
-    mask = __funnelshift_l(e, mask, 2);
+    if (cm_u16(CM)) {  // 16-bit entries: flags in bits 15:14; the shift up is an IMAD (the less loaded pipe)
+      e = lds_tab_u16(da * p.q.kmul + (e & kState));
+      mask = __funnelshift_l(e * 0x10000u, mask, 2);
+      e = lds_tab_u16(db * p.q.kmul + (e & kState));
+      mask = __funnelshift_l(e * 0x10000u, mask, 2);
+    } else {
+      e = lds_tab(da * p.q.kmul + (e & kState));
+      mask = __funnelshift_l(e, mask, 2);
+      e = lds_tab(db * p.q.kmul + (e & kState));
+      mask = __funnelshift_l(e, mask, 2);
+    }
   }
 }
 
@@ -1066,7 +1100,7 @@ __global__ void __launch_bounds__(kL8Threads, 1) lines8_kernel(const Lines8Param
 // ---------------------------------------------------------------------------------------------
 // linesq_kernel: the SWAR modes.  Same tiles, same walks (l8_run / l8_run_ragged), other table image:
 // [kQAbsTrans, +trans_bytes) transition table, brought in by TMA bulk copies, then 2 KB tile buffers.
-// One instantiation per char mode; 24 warps (the table leaves room for 21-22 pairs of tile buffers).
+// One instantiation per char mode; 22 warps (a full-size table leaves room for 21 pairs of tile buffers; 88 registers).
 // ---------------------------------------------------------------------------------------------
 template <int CM>
 __global__ void __launch_bounds__(kQThreads, 1) linesq_kernel(const Lines8Params p) {

@@ -312,13 +312,15 @@ def fast_path(pat, mode, cw):
 
 def test_expected_kernels_are_selected():
     """Guards against silently falling back to a slower kernel on the BASELINE configs.  char_mode >= 16 are the
-    SWAR modes of linesq_kernel: 16 | (K == 4) << 3 | high-byte << 2 | planes."""
+    SWAR modes of linesq_kernel: 16 | 16-bit entries << 5 | (K == 4) << 3 | high-byte << 2 | planes."""
     fp = fast_path(pair(workloads.REGEX["c2"])[0], 2, 1)
     assert fp == {"char_mode": 16 | 8 | 2, "replicated": 32, "has_bwd": 0, "n_cols": 3}  # 4 chars per lookup, 2 compare planes
     fp = fast_path(pair(workloads.REGEX["c3"])[0], 2, 1)
     assert fp["char_mode"] == 0 and fp["replicated"] == 32 and fp["has_bwd"] == 1  # 15 class changes: class map in shared memory
     fp = fast_path(pair(workloads.REGEX["c4"])[0], 2, 1)
     assert fp == {"char_mode": 16 | 2, "replicated": 8, "has_bwd": 0, "n_cols": 4}  # 258 rows: 2 chars per lookup, 8 copies
+    fp = fast_path(pair("a[ab]{7}c|b[ab]{4}d")[0], 2, 1)
+    assert fp["char_mode"] == 16 | 32 | 3 and fp["replicated"] == 8  # 289 rows x 25 columns: 16-bit entries, 3 planes
     fp = fast_path(pair("a[ab]{8}c|b[ab]{6}d")[0], 2, 1)
     assert fp is None or fp["replicated"] in (1, 32)
     fp = fast_path(pair(workloads.REGEX["c5"])[0], 2, 2)
@@ -340,6 +342,7 @@ SWAR_CASES = [
     ("[\x7f]+a", b"a\x7f\x7e\x80\xff"),
     (r"(ab|a|b-)+", b"ab-,.`c"),
     (r"a+b+", b"ab`c"),
+    (r"a[ab]{7}c|b[ab]{4}d", b"aaabbbcd`e"),
 ]
 
 

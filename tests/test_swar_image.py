@@ -22,8 +22,8 @@ def emulate(blob, mode, cw, backward, lane, data, n_chars):
     return rc, {"char_mode": info[0], "copies": info[1], "codes": info[2], "bytes": info[3]}
 
 
-def cm_swar(k, planes, hi):
-    return 16 | (8 if k == 4 else 0) | (4 if hi else 0) | planes
+def cm_swar(k, planes, hi, u16=False):
+    return 16 | (32 if u16 else 0) | (8 if k == 4 else 0) | (4 if hi else 0) | planes
 
 
 def byte_soup(rng, n, hot):
@@ -36,9 +36,9 @@ def byte_soup(rng, n, hot):
 
 
 BYTE_CASES = [
-    # regex, hot alphabet, expected (k, planes, copies, codes) for mode find or None = "just has to be right"
-    (workloads.REGEX["c2"], b"0123456789--- /:,.", (4, 2, 32, 3)),
-    (workloads.REGEX["c4"], b"aaabbbc`d", (2, 2, 8, 4)),
+    # regex, hot alphabet, expected (k, planes, copies, codes, 16-bit entries) for mode find or None = "just has to be right"
+    (workloads.REGEX["c2"], b"0123456789--- /:,.", (4, 2, 32, 3, False)),
+    (workloads.REGEX["c4"], b"aaabbbc`d", (2, 2, 8, 4, False)),
     (r"[0-9]+", b"0123456789/: ", None),
     (r"a*", b"a`b", None),
     (r"[^a]+b", b"ab`c\x7f\x80", None),
@@ -47,6 +47,7 @@ BYTE_CASES = [
     ("x[\x01-\x1f]y", b"xy\x00\x1f\x20\x01", None),
     ("[\x7f]+a", b"a\x7f\x7e\x80\xff", None),
     (r"(ab|a|b-)+", b"ab-,.`c", None),
+    (r"a[ab]{7}c|b[ab]{4}d", b"aaabbbcd`e", (2, 3, 8, 5, True)),
 ]
 
 
@@ -64,8 +65,8 @@ def test_byte_images_walk_like_the_table(regex, hot, expect):
                 if rc == 0:
                     seen += 1
                     if expect and mode == 2:
-                        k, planes, copies, codes = expect
-                        assert info["char_mode"] == cm_swar(k, planes, False) and info["copies"] == copies and info["codes"] == codes, info
+                        k, planes, copies, codes, u16 = expect
+                        assert info["char_mode"] == cm_swar(k, planes, False, u16) and info["copies"] == copies and info["codes"] == codes, info
     assert seen > 0, "no SWAR image for any mode"
     if expect:
         assert emulate(blob, 2, 1, 0, 0, np.zeros(16, dtype=np.uint8), 16)[0] == 0
