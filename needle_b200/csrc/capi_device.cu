@@ -56,6 +56,11 @@ struct Workspace {
   int32_t* start = nullptr;
   int32_t* end = nullptr;
   size_t n_cap = 0;
+  // ndl_find_long: per-tile seam arrays and the scratch record
+  uint32_t* seam_guess = nullptr;
+  uint32_t* seam_exit = nullptr;
+  size_t seam_cap = 0;
+  void* long_scratch = nullptr;
 };
 
 }  // namespace ndl
@@ -116,6 +121,9 @@ static void free_pattern(ndl_pattern* p) {
   cudaFree(p->ws.matched);
   cudaFree(p->ws.start);
   cudaFree(p->ws.end);
+  cudaFree(p->ws.seam_guess);
+  cudaFree(p->ws.seam_exit);
+  cudaFree(p->ws.long_scratch);
   cudaSetDevice(prev);
   delete p;
 }
@@ -158,6 +166,21 @@ static LinesqKernel linesq_kernel_for(int cm) {
 #define NDL_Q16(pl) case cm_swar(2, pl, false, true): return linesq_kernel<cm_swar(2, pl, false, true)>;
     NDL_Q16(1) NDL_Q16(2) NDL_Q16(3)
 #undef NDL_Q16
+    default: return nullptr;
+  }
+}
+
+// The long8_kernel instantiation of a byte char mode (nullptr: not instantiated).
+typedef void (*Long8Kernel)(const Long8Params);
+static Long8Kernel long8_kernel_for(int cm) {
+  switch (cm) {
+    case kCmBytes: return long8_kernel<kCmBytes>;
+    case kCmBytes1: return long8_kernel<kCmBytes1>;
+#define NDL_Q(k, pl, u16) case cm_swar(k, pl, false, u16): return long8_kernel<cm_swar(k, pl, false, u16)>;
+    NDL_Q(4, 1, false) NDL_Q(4, 2, false) NDL_Q(4, 3, false)
+    NDL_Q(2, 1, false) NDL_Q(2, 2, false) NDL_Q(2, 3, false)
+    NDL_Q(2, 1, true) NDL_Q(2, 2, true) NDL_Q(2, 3, true)
+#undef NDL_Q
     default: return nullptr;
   }
 }
@@ -590,11 +613,10 @@ static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, in
     if (n_chars) NDL_CUDA(cudaMemcpyAsync(p->ws.data, data, static_cast<size_t>(n_chars) * char_width, cudaMemcpyHostToDevice, stream));
     d_data = static_cast<const uint8_t*>(p->ws.data);
   }
-  // scratch: SeqResult + 2 atomics + back result
+  // scratch: SeqResult + 2 atomics + back result (kept with the pattern; calls are serialised by ws_mutex)
   struct Scratch { SeqResult r; unsigned long long first_seg, first_bad; int64_t back; };
-  Scratch* d_sc = nullptr;
-  NDL_CUDA(cudaMalloc(&d_sc, sizeof(Scratch)));
-  struct Guard { void* a; void* b; void* c; ~Guard() { cudaFree(a); cudaFree(b); cudaFree(c); } } guard{d_sc, nullptr, nullptr};
+  if (!p->ws.long_scratch) NDL_CUDA(cudaMalloc(&p->ws.long_scratch, sizeof(Scratch)));
+  Scratch* d_sc = static_cast<Scratch*>(p->ws.long_scratch);
   Scratch h;
   const DevTable fwd = p->tables[kForwards].view();
   const int dead = fwd.n_states;
@@ -620,7 +642,8 @@ static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, in
   r.pos = from;
   if (entry_state < 0 || entry_state > dead) return fail(NDL_EINVAL, "entry_state out of range");
   const bool root_acc = p->tables[kForwards].host.root_accepting;
-  const Lines8Blob& img = p->l8[NDL_MODE_FIND];
+  const Lines8Blob& qimg = p->q8[NDL_MODE_FIND];
+  const Lines8Blob& img = qimg.ok && long8_kernel_for(qimg.char_mode) ? qimg : p->l8[NDL_MODE_FIND];
   // the chunk-parallel path is for the search phase (no match seen yet) of a pattern with a non-accepting root
   const bool fast = char_width == 1 && !root_acc && img.ok && from < n && last_init == -1 && entry_state != dead;
 
@@ -634,55 +657,82 @@ static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, in
       last = r.last;
     }
   } else {
+    // canonical state encoding of the image (long8.cuh): state id <-> table entry without flags / copy offset
+    const bool swar = cm_is_swar(img.char_mode);
     const bool s1 = img.char_mode == kCmBytes1;
     const uint32_t row_bytes = img.row_bytes;
-    // head: exact walk up to the first 2 KB boundary
+    const uint32_t eb = swar && cm_u16(img.char_mode) ? 2u : 4u;
+    const uint32_t w_rows = swar ? 128u / eb / static_cast<uint32_t>(img.replicated) : 1u;
+    auto enc = [&](int32_t state) -> uint32_t {
+      const uint32_t st = static_cast<uint32_t>(state);
+      if (swar) return kQAbsTrans + (st / w_rows) * 128u + (st % w_rows) * eb;
+      return s1 ? st : st * row_bytes;
+    };
+    auto dec = [&](uint32_t canon) -> int32_t {
+      if (swar) {
+        const uint32_t off = canon - kQAbsTrans;
+        return static_cast<int32_t>((off / 128u) * w_rows + (off % 128u) / eb);
+      }
+      return static_cast<int32_t>(s1 ? canon : canon / row_bytes);
+    };
+    // head: exact walk up to the first 16-byte boundary
     const uintptr_t a0 = reinterpret_cast<uintptr_t>(d_data) + static_cast<uintptr_t>(from);
-    int64_t head_end = from + static_cast<int64_t>(((a0 + 2047) & ~static_cast<uintptr_t>(2047)) - a0);
+    int64_t head_end = from + static_cast<int64_t>(((a0 + 15) & ~static_cast<uintptr_t>(15)) - a0);
     if (head_end > n) head_end = n;
-    if ((rc = seq(from, head_end, entry_state, from, -1, r)) != NDL_OK) return rc;
     bool done = false;
-    if (r.state == dead) {
-      last = r.last;
-      done = true;
-    } else if (r.last != -1) {  // a match began in the head and may run on: follow it to its end
-      SeqResult r2;
-      if ((rc = seq(head_end, n, r.state, head_end, r.last, r2)) != NDL_OK) return rc;
-      last = r2.last;
-      r = r2;
-      done = true;
+    if (head_end > from) {
+      if ((rc = seq(from, head_end, entry_state, from, -1, r)) != NDL_OK) return rc;
+      if (r.state == dead) {
+        last = r.last;
+        done = true;
+      } else if (r.last != -1) {  // a match began in the head and may run on: follow it to its end
+        SeqResult r2;
+        if ((rc = seq(head_end, n, r.state, head_end, r.last, r2)) != NDL_OK) return rc;
+        last = r2.last;
+        r = r2;
+        done = true;
+      }
     }
     if (!done) {
-      const uint64_t n_tiles = static_cast<uint64_t>(n - head_end) / 2048;
+      const uint64_t n_segs = static_cast<uint64_t>(n - head_end) / kLongSeg;
+      const uint64_t n_tiles = (n_segs + 31) / 32;
       int32_t state = r.state;
       int64_t pos = head_end;
-      if (n_tiles > 0) {
-        uint32_t *d_guess = nullptr, *d_exit = nullptr;
-        NDL_CUDA(cudaMalloc(&d_guess, n_tiles * sizeof(uint32_t)));
-        guard.b = d_guess;
-        NDL_CUDA(cudaMalloc(&d_exit, n_tiles * sizeof(uint32_t)));
-        guard.c = d_exit;
+      if (n_segs > 0) {
+        Workspace& ws = p->ws;
+        if (n_tiles > ws.seam_cap) {
+          cudaFree(ws.seam_guess);
+          cudaFree(ws.seam_exit);
+          ws.seam_guess = ws.seam_exit = nullptr;
+          ws.seam_cap = 0;
+          const size_t cap = n_tiles + n_tiles / 8 + 16;
+          NDL_CUDA(cudaMalloc(&ws.seam_guess, cap * sizeof(uint32_t)));
+          NDL_CUDA(cudaMalloc(&ws.seam_exit, cap * sizeof(uint32_t)));
+          ws.seam_cap = cap;
+        }
         NDL_CUDA(cudaMemsetAsync(&d_sc->first_seg, 0xff, 2 * sizeof(unsigned long long), stream));
         Long8Params lp;
         lp.data = d_data + head_end;
-        lp.n_tiles = n_tiles;
+        lp.n_segs = n_segs;
         lp.image = img.dev;
         lp.trans_bytes = img.trans_bytes;
         lp.root_entry = img.root_entry;
         lp.row_bytes = row_bytes;
-        lp.entry0 = s1 ? static_cast<uint32_t>(r.state) : static_cast<uint32_t>(r.state) * row_bytes;
-        lp.seam_guess = d_guess;
-        lp.seam_exit = d_exit;
+        lp.entry0 = enc(r.state);
+        lp.q = img.q;
+        lp.seam_guess = ws.seam_guess;
+        lp.seam_exit = ws.seam_exit;
         lp.first_seg = &d_sc->first_seg;
         lp.first_bad = &d_sc->first_bad;
-        auto kern = s1 ? long8_kernel<kCmBytes1> : long8_kernel<kCmBytes>;
+        Long8Kernel kern = long8_kernel_for(img.char_mode);
         NDL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kL8DynSmem));
-        uint64_t want = (n_tiles + kL8Warps - 1) / kL8Warps;
+        const uint32_t block_warps = swar ? kQWarps : kL8Warps;
+        uint64_t want = (n_tiles + block_warps - 1) / block_warps;
         int blocks = static_cast<int>(want < static_cast<uint64_t>(p->sm_count) ? want : p->sm_count);
-        kern<<<blocks, kL8Threads, kL8DynSmem, stream>>>(lp);
+        kern<<<blocks, block_warps * 32, kL8DynSmem, stream>>>(lp);
         g_launches.fetch_add(1);
         NDL_CUDA(cudaGetLastError());
-        long8_seam_kernel<<<p->sm_count * 4, 256, 0, stream>>>(d_guess, d_exit, n_tiles, &d_sc->first_bad);
+        long8_seam_kernel<<<p->sm_count * 4, 256, 0, stream>>>(ws.seam_guess, ws.seam_exit, n_tiles, &d_sc->first_bad);
         g_launches.fetch_add(1);
         NDL_CUDA(cudaGetLastError());
         NDL_CUDA(cudaMemcpyAsync(&h, d_sc, sizeof(Scratch), cudaMemcpyDeviceToHost, stream));
@@ -696,7 +746,7 @@ static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, in
           done = true;
         } else if (h.first_seg != kNone) {
           // exact re-walk from the start of the first accepting segment
-          pos = head_end + static_cast<int64_t>(h.first_seg) * 64;
+          pos = head_end + static_cast<int64_t>(h.first_seg) * kLongSeg;
           if (h.first_seg != 0) {
             SeqResult w;
             if ((rc = seq(pos - 16, pos, 0, pos, -1, w)) != NDL_OK) return rc;  // the verified guess
@@ -706,17 +756,23 @@ static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, in
           last = r.last;
           done = true;
         } else {
-          // no match in the tiles: continue exactly from the (verified) exit of the last tile
-          uint32_t exit_off = 0;
-          NDL_CUDA(cudaMemcpyAsync(&exit_off, d_exit + (n_tiles - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+          // no match in the segments: continue exactly from the (verified) exit of the last one
+          uint32_t exit_canon = 0;
+          NDL_CUDA(cudaMemcpyAsync(&exit_canon, ws.seam_exit + (n_tiles - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
           NDL_CUDA(cudaStreamSynchronize(stream));
-          state = static_cast<int32_t>(s1 ? exit_off : exit_off / row_bytes);
-          pos = head_end + static_cast<int64_t>(n_tiles) * 2048;
+          state = dec(exit_canon);
+          pos = head_end + static_cast<int64_t>(n_segs) * kLongSeg;
         }
       }
       if (!done) {
-        if ((rc = seq(pos, n, state, pos, -1, r)) != NDL_OK) return rc;
-        last = r.last;
+        if (pos < n) {
+          if ((rc = seq(pos, n, state, pos, -1, r)) != NDL_OK) return rc;
+          last = r.last;
+        } else {
+          r.state = state;
+          r.pos = pos;
+          last = -1;
+        }
       }
     }
   }

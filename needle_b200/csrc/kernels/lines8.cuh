@@ -598,7 +598,7 @@ __device__ __forceinline__ uint32_t lds_tab_u16(uint32_t addr) {
 }
 
 template <int CM, bool REV>
-__device__ __forceinline__ void q_word(uint32_t w, const Lines8Params& p, uint32_t& e, uint32_t& mask) {
+__device__ __forceinline__ void q_word(uint32_t w, const SwarDev& q, uint32_t& e, uint32_t& mask) {
   constexpr int P = cm_planes(CM), K = cm_k(CM);
   constexpr uint32_t kState = L8Enc<CM>::kStateMask;
   const uint32_t w80 = w | 0x80808080u;
@@ -606,29 +606,29 @@ __device__ __forceinline__ void q_word(uint32_t w, const Lines8Params& p, uint32
   asm("lop3.b32 %0, %1, 0x80808080, 0, 0x0c;" : "=r"(nm) : "r"(w));  // ~w & 0x80808080 (LUT: ~a & b)
   uint32_t pl[P];
 #pragma unroll
-  for (int i = 0; i < P; i++) pl[i] = ((w80 - p.q.lo[i]) ^ (w80 - p.q.hi[i])) & nm;
+  for (int i = 0; i < P; i++) pl[i] = ((w80 - q.lo[i]) ^ (w80 - q.hi[i])) & nm;
   if (K == 4) {
     uint32_t dp = 0;
 #pragma unroll
-    for (int i = 0; i < P; i++) dp = __dp4a(pl[i], p.q.w[i][REV ? 2 : 0], dp);
-    e = lds_tab(dp * p.q.kmul + (e & kState));
+    for (int i = 0; i < P; i++) dp = __dp4a(pl[i], q.w[i][REV ? 2 : 0], dp);
+    e = lds_tab(dp * q.kmul + (e & kState));
     mask = __funnelshift_l(e, mask, 4);
   } else {
     uint32_t da = 0, db = 0;
 #pragma unroll
     for (int i = 0; i < P; i++) {
-      da = __dp4a(pl[i], p.q.w[i][REV ? 2 : 0], da);
-      db = __dp4a(pl[i], p.q.w[i][REV ? 3 : 1], db);
+      da = __dp4a(pl[i], q.w[i][REV ? 2 : 0], da);
+      db = __dp4a(pl[i], q.w[i][REV ? 3 : 1], db);
     }
     if (cm_u16(CM)) {  // 16-bit entries: flags in bits 15:14; the shift up is an IMAD (the less loaded pipe)
-      e = lds_tab_u16(da * p.q.kmul + (e & kState));
+      e = lds_tab_u16(da * q.kmul + (e & kState));
       mask = __funnelshift_l(e * 0x10000u, mask, 2);
-      e = lds_tab_u16(db * p.q.kmul + (e & kState));
+      e = lds_tab_u16(db * q.kmul + (e & kState));
       mask = __funnelshift_l(e * 0x10000u, mask, 2);
     } else {
-      e = lds_tab(da * p.q.kmul + (e & kState));
+      e = lds_tab(da * q.kmul + (e & kState));
       mask = __funnelshift_l(e, mask, 2);
-      e = lds_tab(db * p.q.kmul + (e & kState));
+      e = lds_tab(db * q.kmul + (e & kState));
       mask = __funnelshift_l(e, mask, 2);
     }
   }
@@ -637,16 +637,16 @@ __device__ __forceinline__ void q_word(uint32_t w, const Lines8Params& p, uint32
 // All chars of one 16-byte chunk, forwards / backwards.  Afterwards the low L8Chars<CM>::kPerChunk bits of
 // `mask` are the accept flags of these chars, bit 0 = the char walked last.
 template <int CM>
-__device__ __forceinline__ void l8_chunk(const uint4& w, const Lines8Params& p, const L8Ctx& cx, uint32_t& e, uint32_t& mask) {
+__device__ __forceinline__ void l8_chunk(const uint4& w, const SwarDev& q, const L8Ctx& cx, uint32_t& e, uint32_t& mask) {
   if constexpr (cm_is_swar(CM)) {
     if constexpr (cm_hi(CM)) {
-      q_word<CM, false>(__byte_perm(w.x, w.y, 0x7531), p, e, mask);
-      q_word<CM, false>(__byte_perm(w.z, w.w, 0x7531), p, e, mask);
+      q_word<CM, false>(__byte_perm(w.x, w.y, 0x7531), q, e, mask);
+      q_word<CM, false>(__byte_perm(w.z, w.w, 0x7531), q, e, mask);
     } else {
-      q_word<CM, false>(w.x, p, e, mask);
-      q_word<CM, false>(w.y, p, e, mask);
-      q_word<CM, false>(w.z, p, e, mask);
-      q_word<CM, false>(w.w, p, e, mask);
+      q_word<CM, false>(w.x, q, e, mask);
+      q_word<CM, false>(w.y, q, e, mask);
+      q_word<CM, false>(w.z, q, e, mask);
+      q_word<CM, false>(w.w, q, e, mask);
     }
   } else {
     l8_word<CM>(w.x, cx, e, mask);
@@ -656,16 +656,16 @@ __device__ __forceinline__ void l8_chunk(const uint4& w, const Lines8Params& p, 
   }
 }
 template <int CM>
-__device__ __forceinline__ void l8_chunk_rev(const uint4& w, const Lines8Params& p, const L8Ctx& cx, uint32_t& e, uint32_t& mask) {
+__device__ __forceinline__ void l8_chunk_rev(const uint4& w, const SwarDev& q, const L8Ctx& cx, uint32_t& e, uint32_t& mask) {
   if constexpr (cm_is_swar(CM)) {
     if constexpr (cm_hi(CM)) {
-      q_word<CM, true>(__byte_perm(w.z, w.w, 0x7531), p, e, mask);
-      q_word<CM, true>(__byte_perm(w.x, w.y, 0x7531), p, e, mask);
+      q_word<CM, true>(__byte_perm(w.z, w.w, 0x7531), q, e, mask);
+      q_word<CM, true>(__byte_perm(w.x, w.y, 0x7531), q, e, mask);
     } else {
-      q_word<CM, true>(w.w, p, e, mask);
-      q_word<CM, true>(w.z, p, e, mask);
-      q_word<CM, true>(w.y, p, e, mask);
-      q_word<CM, true>(w.x, p, e, mask);
+      q_word<CM, true>(w.w, q, e, mask);
+      q_word<CM, true>(w.z, q, e, mask);
+      q_word<CM, true>(w.y, q, e, mask);
+      q_word<CM, true>(w.x, q, e, mask);
     }
   } else {
     l8_word_rev<CM>(w.w, cx, e, mask);
@@ -705,7 +705,7 @@ __device__ __forceinline__ int32_t l8_reverse(const Lines8Params& p, ChunkAddr c
     const uint4 x = lds_data16(chunk_addr(q > 0 ? q - 1 : 0));
     const uint4 w = L8Align(h & 15u).apply(x, y);
     uint32_t mask = 0;
-    l8_chunk_rev<CM>(w, p, cx, e, mask);
+    l8_chunk_rev<CM>(w, p.q, cx, e, mask);
     const int32_t valid = rem < kPer ? rem : kPer;
     mask >>= (kPer - valid);  // drop the steps taken before the start of the line
     const int32_t cand = rem - valid + (__ffs(mask) - 1);
@@ -857,7 +857,7 @@ __device__ __forceinline__ void l8_run(const Lines8Params& p, const L8Ctx& cx, c
 #pragma unroll
         for (uint32_t c = 0; c < G::kCpl; c++) {
           const uint4 w = lds_data16(cur + (l8_slot(lane, c, LOG2CPL) << 4));
-          l8_chunk<CM>(w, p, cx, e, mask);
+          l8_chunk<CM>(w, p.q, cx, e, mask);
           constexpr uint32_t kFlush = 32 / kPer;  // chunks whose accept bits fit in the 32-bit mask
           if ((c % kFlush) == kFlush - 1 || c + 1 == G::kCpl) {  // bit 0 = the most recent char
             const int32_t cand = static_cast<int32_t>((c + 1) * kPer + 1) - __ffs(mask);
@@ -971,7 +971,7 @@ __device__ __forceinline__ void l8_run_ragged(const Lines8Params& p, const L8Ctx
         const uint4 y = lds_data16(cur + l8_rslot(c0 + (pos / kPer) + 1));
         const uint4 w = al.apply(x, y);
         uint32_t mask = 0;
-        l8_chunk<CM>(w, p, cx, e, mask);
+        l8_chunk<CM>(w, p.q, cx, e, mask);
         const uint32_t valid = min(kPer, len - pos);
         mask >>= (kPer - valid);  // drop the accept bits of chars past the end of the line
         const int32_t cand = static_cast<int32_t>(pos + valid + 1) - __ffs(mask);

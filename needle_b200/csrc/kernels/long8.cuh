@@ -2,9 +2,9 @@
 //
 // A DFA walk is sequential, but an unanchored search DFA forgets: while no match has been seen its state
 // is (for most patterns) a function of the last few chars only, because every non-accepting state carries
-// the restart thread (NFAToDFACompiler.java:70-72, 108-112).  So the haystack is cut into 64-byte
-// segments, one per lane, 32 per warp tile (the same swizzled shared-memory tiles and pair tables as
-// lines8), and every lane
+// the restart thread (NFAToDFACompiler.java:70-72, 108-112).  So the haystack is cut into 256-byte
+// segments, one per lane, 32 per warp tile (staged as 64-byte pieces through the same swizzled shared-memory
+// tiles, walked with the same table images as lines8 / linesq), and every lane
 //   1. guesses its entry state by walking the 16 bytes before its segment from the root,
 //   2. walks its segment from that guess, recording its exit state and whether it saw an accepting state,
 //   3. checks, by warp shuffle, that the exit state of the lane before it equals its own guess
@@ -87,119 +87,161 @@ __global__ void seq_back_from_kernel(BatchParams g, const CharT* s, int64_t inde
   out[1] = state;
 }
 
+constexpr uint32_t kLongSeg = 256;  // bytes per segment = per lane and tile
+
 struct Long8Params {
-  const uint8_t* data;     // 2048-byte aligned start of tile 0
-  uint64_t n_tiles;        // full 2 KB tiles
-  const uint8_t* image;    // lines8 image of the FORWARDS table
+  const uint8_t* data;     // 16-byte aligned start of segment 0
+  uint64_t n_segs;         // 256-byte segments; 32 per tile, the last tile may be partial
+  const uint8_t* image;    // lines8 / linesq image of the FORWARDS table
   uint32_t trans_bytes;
   uint32_t root_entry;
   uint32_t row_bytes;      // kCmBytes1 layout
-  uint32_t entry0;         // exact entry of tile 0, lane 0 (same encoding as the table entries, flags clear)
-  uint32_t* seam_guess;    // [n_tiles] lane 0's guessed entry
-  uint32_t* seam_exit;     // [n_tiles] lane 31's exit
+  uint32_t entry0;         // exact entry of segment 0 in the canonical encoding (see canon())
+  SwarDev q;               // SWAR modes
+  uint32_t* seam_guess;    // [n_tiles] lane 0's guessed entry (canonical)
+  uint32_t* seam_exit;     // [n_tiles] exit of the tile's last segment (canonical)
   unsigned long long* first_seg;   // atomicMin: first segment (global index) that saw an accepting state
   unsigned long long* first_bad;   // atomicMin: first segment whose in-warp check failed
 };
 
+// A lane owns 256 contiguous bytes of a tile and walks them as four 64-byte pieces through the usual swizzled
+// 2 KB warp buffers (double buffered across pieces and tiles), so only 16 of every 272 bytes walked are warm-up.
+// States are compared across lanes in a canonical encoding: the table entry without flags and - in the SWAR
+// layouts, where every lane addresses its own table copy - without the lane's copy offset.
 template <int CM>
-__global__ void __launch_bounds__(kL8Threads, 1) long8_kernel(const Long8Params p) {
+__global__ void __launch_bounds__(cm_is_swar(CM) ? kQThreads : kL8Threads, 1) long8_kernel(const Long8Params p) {
+  constexpr bool kSwar = cm_is_swar(CM);
+  constexpr uint32_t kBlockWarps = kSwar ? kQWarps : kL8Warps;
+  constexpr uint32_t kStateMask = L8Enc<CM>::kStateMask;
   const uint32_t tid = threadIdx.x;
   const uint32_t lane = tid & 31, warp = tid >> 5;
-  L8Setup su(CM == kCmBytes1, warp);
-  const uint32_t buf0 = su.buf0, buf1 = su.buf1;
+  bool layout_ok;
+  uint32_t buf0, buf1, usable_warps;
+  if constexpr (kSwar) {
+    extern __shared__ __align__(128) uint8_t l8_dyn_smem[];
+    const uint32_t base = static_cast<uint32_t>(__cvta_generic_to_shared(l8_dyn_smem));
+    layout_ok = base <= kQAbsTrans;
+    const uint32_t tiles_lo = (kQAbsTrans + p.trans_bytes + 127u) & ~127u;
+    usable_warps = min(kBlockWarps, (kL8AbsBar - tiles_lo) / kL8WarpBuf / 2);
+    buf0 = tiles_lo + 2 * warp * kL8WarpBuf;
+    buf1 = buf0 + kL8WarpBuf;
+  } else {
+    L8Setup su(CM == kCmBytes1, warp);
+    layout_ok = su.layout_ok;
+    usable_warps = su.usable_warps;
+    buf0 = su.buf0;
+    buf1 = su.buf1;
+  }
   if (tid == 0) {
     mbar_init(kL8AbsBar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  if (!su.layout_ok) {  // cannot happen with the launch configuration used; report every tile as unverified
+  if (!layout_ok) {  // cannot happen with the launch configuration used; report every tile as unverified
     if (tid == 0 && blockIdx.x == 0) atomicMin(p.first_bad, 0ull);
     return;
   }
   if (tid == 0) {
-    mbar_expect_tx(kL8AbsBar, su.cmap_bytes + p.trans_bytes);
-    tma_bulk_g2s(kL8AbsCmap, p.image, su.cmap_bytes, kL8AbsBar);
-    tma_bulk_g2s(su.abs_trans, p.image + su.cmap_bytes, p.trans_bytes, kL8AbsBar);
+    if constexpr (kSwar) {
+      mbar_expect_tx(kL8AbsBar, p.trans_bytes);
+      for (uint32_t off = 0; off < p.trans_bytes; off += 0x8000u)
+        tma_bulk_g2s(kQAbsTrans + off, p.image + off, min(0x8000u, p.trans_bytes - off), kL8AbsBar);
+    } else {
+      const uint32_t cmap_bytes = CM == kCmBytes1 ? kS1CmapBytes : kL8CmapBytes;
+      mbar_expect_tx(kL8AbsBar, cmap_bytes + p.trans_bytes);
+      tma_bulk_g2s(kL8AbsCmap, p.image, cmap_bytes, kL8AbsBar);
+      tma_bulk_g2s(CM == kCmBytes1 ? kS1AbsTrans : kL8AbsTrans, p.image + cmap_bytes, p.trans_bytes, kL8AbsBar);
+    }
   }
-  constexpr int LOG2CPL = 2;  // 64-byte segments
+  constexpr int LOG2CPL = 2;  // 64-byte pieces
   uint32_t dst_off[4];
 #pragma unroll
   for (uint32_t k = 0; k < 4; k++) {
     const uint32_t c = lane + 32 * k;
     dst_off[k] = l8_slot(c >> LOG2CPL, c & 3, LOG2CPL) << 4;
   }
+  const uint32_t lane_off = kSwar ? (lane & p.q.copy_mask) * p.q.copy_bytes : 0u;
   L8Ctx cx;
   cx.sel_a = 0x00010000u | (lane * 4);
   cx.sel_b = cx.sel_a | 0x80u;
   cx.page1 = cx.page3 = cx.ua = cx.ub = cx.xa = cx.xb = 0;
   cx.row_bytes = p.row_bytes;
-  auto stage = [&](uint64_t t, uint32_t buf) {
-    const uint8_t* src = p.data + t * 2048 + lane * 16;
+  cx.root = p.root_entry + lane_off;
+  cx.bwd_root = cx.bwd_dead = 0;
+  const uint64_t n_tiles = (p.n_segs + 31) / 32;
+  // piece j of tile t: lane's copies are 16-byte chunks c = lane + 32 k of the piece, chunk c = part (c & 3) of segment (c >> 2)
+  auto stage = [&](uint64_t t, uint32_t j, uint32_t buf) {
+    const uint64_t seg0 = t * 32;
+    const uint32_t segs_here = static_cast<uint32_t>(min(static_cast<uint64_t>(32), p.n_segs - seg0));
+    const uint8_t* src = p.data + seg0 * kLongSeg + j * 64 + (lane >> 2) * kLongSeg + (lane & 3) * 16;
 #pragma unroll
-    for (uint32_t k = 0; k < 4; k++) cp_async16(buf + dst_off[k], src + 512 * k);
+    for (uint32_t k = 0; k < 4; k++)
+      if ((lane >> 2) + 8 * k < segs_here) cp_async16(buf + dst_off[k], src + 8 * k * kLongSeg);
     cp_async_commit();
   };
-  const uint64_t n_warps = static_cast<uint64_t>(gridDim.x) * su.usable_warps;
-  uint64_t t = static_cast<uint64_t>(blockIdx.x) * su.usable_warps + warp;
+  const uint64_t n_warps = static_cast<uint64_t>(gridDim.x) * usable_warps;
+  uint64_t t = static_cast<uint64_t>(blockIdx.x) * usable_warps + warp;
   uint32_t cur = buf0, nxt = buf1;
   mbar_wait(kL8AbsBar, 0);
-  if (!su.warp_ok) return;  // no pair of tile buffers for this warp in this layout
-  if (t < p.n_tiles) stage(t, cur);
+  if (warp >= usable_warps) return;  // no pair of tile buffers for this warp in this layout
+  if (t < n_tiles) stage(t, 0, cur);
 
-  for (; t < p.n_tiles; t += n_warps) {
-    if (t + n_warps < p.n_tiles) stage(t + n_warps, nxt);
-    else cp_async_commit();
-    // lane 0's warm-up bytes are the last 16 bytes of the previous tile: fetch them while the copy lands
-    uint4 pre = make_uint4(0, 0, 0, 0);
-    if (lane == 0 && t > 0) pre = *reinterpret_cast<const uint4*>(p.data + t * 2048 - 16);
-    cp_async_wait<1>();
-    __syncwarp();
-    // a match in an earlier segment makes this tile irrelevant
-    const unsigned long long seg0 = t * 32ull;
-    if (*reinterpret_cast<volatile unsigned long long*>(p.first_seg) >= seg0) {
-      // 1. guess: 16 bytes before the segment, from the root
-      if (lane != 0) pre = lds_data16(cur + (l8_slot(lane - 1, 3, LOG2CPL) << 4));
-      uint32_t e = p.root_entry, mask = 0;
-      l8_word<CM>(pre.x, cx, e, mask);
-      l8_word<CM>(pre.y, cx, e, mask);
-      l8_word<CM>(pre.z, cx, e, mask);
-      l8_word<CM>(pre.w, cx, e, mask);
-      if (lane == 0 && t == 0) e = p.entry0;  // the head was walked exactly
-      constexpr uint32_t kStateMask = CM == kCmBytes1 ? 0x7fffu : kL8FlagMask;
-      const uint32_t guess = e & kStateMask;
-      // 2. the segment itself
-      uint32_t any = 0;
-#pragma unroll
-      for (uint32_t c = 0; c < 4; c++) {
-        const uint4 w = lds_data16(cur + (l8_slot(lane, c, LOG2CPL) << 4));
-        mask = 0;
-        l8_word<CM>(w.x, cx, e, mask);
-        l8_word<CM>(w.y, cx, e, mask);
-        l8_word<CM>(w.z, cx, e, mask);
-        l8_word<CM>(w.w, cx, e, mask);
-        any |= mask;
-      }
-      const uint32_t exit_state = e & kStateMask;
-      // 3. in-warp check + seams
-      const uint32_t prev_exit = __shfl_up_sync(0xffffffffu, exit_state, 1);
-      const bool bad = lane != 0 && prev_exit != guess;
-      const uint32_t bad_lanes = __ballot_sync(0xffffffffu, bad);
-      const uint32_t acc_lanes = __ballot_sync(0xffffffffu, any != 0);
-      if (lane == 0) {
-        p.seam_guess[t] = guess;
-        if (bad_lanes) atomicMin(p.first_bad, seg0 + (__ffs(bad_lanes) - 1));
-        if (acc_lanes) atomicMin(p.first_seg, seg0 + (__ffs(acc_lanes) - 1));
-      }
-      if (lane == 31) p.seam_exit[t] = exit_state;
-    } else if (lane == 0) {
-      p.seam_guess[t] = 0xffffffffu;  // skipped: not part of the verified prefix
-      p.seam_exit[t] = 0xfffffffeu;
+  for (; t < n_tiles; t += n_warps) {
+    const uint64_t seg0 = t * 32;
+    const uint32_t segs_here = static_cast<uint32_t>(min(static_cast<uint64_t>(32), p.n_segs - seg0));
+    const bool act = lane < segs_here;
+    // a match in an earlier segment makes this tile - and every later one of this warp - irrelevant
+    if (*reinterpret_cast<volatile unsigned long long*>(p.first_seg) < seg0) {
+      if (lane == 0)
+        for (uint64_t u = t; u < n_tiles; u += n_warps) {
+          p.seam_guess[u] = 0xffffffffu;  // skipped: not part of the verified prefix
+          p.seam_exit[u] = 0xfffffffeu;
+        }
+      break;
     }
-    __syncwarp();
-    const uint32_t tmp = cur;
-    cur = nxt;
-    nxt = tmp;
+    // warm-up bytes: the 16 bytes before the lane's segment, straight from global memory
+    uint4 pre = make_uint4(0, 0, 0, 0);
+    if (act && (seg0 + lane) != 0) pre = *reinterpret_cast<const uint4*>(p.data + (seg0 + lane) * kLongSeg - 16);
+    uint32_t e = cx.root, mask = 0, any = 0, guess = 0;
+#pragma unroll 1
+    for (uint32_t j = 0; j < 4; j++) {
+      if (j < 3) stage(t, j + 1, nxt);
+      else if (t + n_warps < n_tiles) stage(t + n_warps, 0, nxt);
+      else cp_async_commit();
+      cp_async_wait<1>();
+      __syncwarp();
+      if (act) {
+        if (j == 0) {  // 1. guess the entry state
+          l8_chunk<CM>(pre, p.q, cx, e, mask);
+          if (seg0 + lane == 0) e = p.entry0 + lane_off;  // the head was walked exactly
+          guess = (e & kStateMask) - lane_off;
+        }
+#pragma unroll
+        for (uint32_t c = 0; c < 4; c++) {  // 2. the piece itself
+          const uint4 w = lds_data16(cur + (l8_slot(lane, c, LOG2CPL) << 4));
+          mask = 0;
+          l8_chunk<CM>(w, p.q, cx, e, mask);
+          any |= mask;
+        }
+      }
+      __syncwarp();
+      const uint32_t tmp = cur;
+      cur = nxt;
+      nxt = tmp;
+    }
+    // 3. in-warp check + seams
+    const uint32_t exit_state = (e & kStateMask) - lane_off;
+    const uint32_t prev_exit = __shfl_up_sync(0xffffffffu, exit_state, 1);
+    const bool bad = act && lane != 0 && prev_exit != guess;
+    const uint32_t bad_lanes = __ballot_sync(0xffffffffu, bad);
+    const uint32_t acc_lanes = __ballot_sync(0xffffffffu, act && any != 0);
+    if (lane == 0) {
+      p.seam_guess[t] = guess;
+      if (bad_lanes) atomicMin(p.first_bad, static_cast<unsigned long long>(seg0 + (__ffs(bad_lanes) - 1)));
+      if (acc_lanes) atomicMin(p.first_seg, static_cast<unsigned long long>(seg0 + (__ffs(acc_lanes) - 1)));
+    }
+    if (lane == segs_here - 1) p.seam_exit[t] = exit_state;
   }
   cp_async_wait<0>();
 }

@@ -34,7 +34,8 @@ def ab_buffer(n, seed):
     return (rng.integers(0, 2, size=n, dtype=np.uint8) + ord("a")).astype(np.uint8)
 
 
-@pytest.mark.parametrize("n", [0, 1, 8, 9, 10, 100, 2047, 2048, 2049, 4096 + 9, 70_001, 3_000_000])
+@pytest.mark.parametrize("n", [0, 1, 8, 9, 10, 100, 255, 256, 257, 271, 272, 273, 2047, 2048, 2049, 4096 + 9, 8191, 8192, 8193, 8192 + 255,
+                               8192 + 256 + 17, 70_001, 3_000_000])
 def test_c4_match_at_the_very_end(n):
     pat, ora = pair(workloads.REGEX["c4"])
     data = ab_buffer(n, n)
@@ -51,7 +52,8 @@ def test_c4_match_positions_across_segment_and_tile_boundaries():
     pat, ora = pair(workloads.REGEX["c4"])
     n = 300_000
     base = ab_buffer(n, 3)
-    for pos in [0, 1, 55, 56, 63, 64, 2040, 2047, 2048, 2050, 4090, 65_530, 131_072 - 4, 250_000, n - 9]:
+    for pos in [0, 1, 55, 56, 63, 64, 240, 247, 248, 255, 256, 2040, 2047, 2048, 2050, 4090, 8184, 8190, 8192, 65_530, 131_072 - 4, 250_000,
+                n - 9]:
         data = base.copy()
         data[pos] = ord("a")
         data[pos + 8] = ord("c")
