@@ -186,12 +186,14 @@ static Long8Kernel long8_kernel_for(int cm) {
 }
 
 static void fill_lines8_params(Lines8Params& lp, const BatchParams& bp, const Lines8Blob& img) {
+  std::memset(&lp, 0, sizeof(lp));
   lp.g = bp;
   lp.image = img.dev;
   lp.trans_bytes = img.trans_bytes;
   lp.root_entry = img.root_entry;
   lp.bwd_root = img.bwd_root;
   lp.bwd_dead = img.bwd_dead;
+  lp.fwd_dead = img.fwd_dead;
   lp.ua = img.ua;
   lp.ub = img.ub;
   lp.xa = img.xa;

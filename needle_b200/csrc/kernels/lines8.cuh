@@ -127,6 +127,7 @@ struct Lines8Blob {
   uint32_t root_entry = 0;   // E of "currently in the root state" (forward table)
   uint32_t bwd_root = 0;     // same for the BACKWARDS table, when resident
   uint32_t bwd_dead = 0;     // row offset of its DEAD row
+  uint32_t fwd_dead = 0;     // DEAD row of the forward table, same encoding as root_entry
   uint32_t ua = 0, ub = 0;   // kCmMixed: CA / CB value of the class every other page has
   uint32_t xa = 0, xb = 0;   // UTF-16 modes: CA / CB value of the class of U+FFFF
   int mixed_page = 0;        // kCmMixed: the high byte of the non-uniform page
@@ -228,6 +229,7 @@ inline bool lines8_layout(const HostDeviceTable& f, const HostDeviceTable* b, in
   };
   emit(f, 0, false);
   meta.root_entry = 0;  // forward root = row 0
+  meta.fwd_dead = static_cast<uint32_t>(f.n_states) * row_bytes;
   meta.has_bwd = b != nullptr;
   if (b) {
     emit(*b, rows_f, true);
@@ -281,6 +283,7 @@ inline bool lines8_layout_s1(const HostDeviceTable& f, std::vector<uint8_t>& img
   meta = Lines8Blob();
   meta.trans_bytes = trans_bytes;
   meta.root_entry = 0;
+  meta.fwd_dead = static_cast<uint32_t>(f.n_states);
   meta.replicated = 32;
   meta.n_cols = C;
   meta.row_bytes = row_bytes;
@@ -406,6 +409,7 @@ inline bool linesq_layout(const HostDeviceTable& f, const HostDeviceTable* b, in
     meta.bwd_dead = kQAbsTrans + slot_off(static_cast<uint32_t>(rows_f + b->n_states), 0);
   }
   meta.root_entry = kQAbsTrans;
+  meta.fwd_dead = kQAbsTrans + slot_off(static_cast<uint32_t>(f.n_states), 0);
   meta.trans_bytes = trans_bytes;
   meta.replicated = R;
   meta.n_cols = n;
@@ -440,7 +444,7 @@ struct Lines8Params {
   const uint8_t* image;  // [cmap][trans]
   uint32_t trans_bytes;
   uint32_t root_entry;
-  uint32_t bwd_root, bwd_dead;
+  uint32_t bwd_root, bwd_dead, fwd_dead;
   uint32_t ua, ub;       // kCmMixed
   uint32_t xa, xb;       // UTF-16 modes: U+FFFF
   int mixed_page;
@@ -507,6 +511,7 @@ struct L8Ctx {
   uint32_t row_bytes;     // kCmBytes1
   uint32_t root;          // entry value of "in the root state" (SWAR modes: this lane's copy)
   uint32_t bwd_root, bwd_dead;  // the same for the BACKWARDS rows; row of its DEAD state
+  uint32_t fwd_dead;            // DEAD row of the forward table
 };
 
 // How a table entry encodes state and accept flags, per char mode.
@@ -886,14 +891,35 @@ __device__ __forceinline__ void l8_run(const Lines8Params& p, const L8Ctx& cx, c
 }
 
 // ---------------------------------------------------------------------------------------------
-// Ragged lines: a warp tile is the longest run of <= 32 consecutive lines whose bytes (from the 16-byte
-// boundary below the first line) fit in the warp's 2 KB buffer.  Chunks are stored XOR-swizzled by
-// (chunk >> 3) so that lines of about 64 bytes still read conflict free.  A lane reads its line as
-// aligned 16-byte chunks and realigns them in registers (word select by the start offset, then funnel
-// shifts).  The walk simply runs over whole 16-byte windows: chars past the end of a line only produce
-// accept bits past the end, which are shifted out, so no per-char bounds test is needed.
+// Ragged lines.  A warp tile is the longest run of <= 32 consecutive lines whose bytes (from the 16-byte
+// boundary below the first line) fit in a 2 KB buffer; chunks are stored XOR-swizzled by (chunk >> 3) so that
+// lines of about 64 bytes still read conflict free.  A lane reads its line as aligned 16-byte chunks and
+// realigns them in registers (word select by the start offset, then funnel shifts).  The walk runs over whole
+// 16-byte windows: chars past the end of a line only produce accept bits past the end, which are shifted out,
+// so no per-char bounds test is needed.
+//
+// One line per lane would leave half the lanes idle (a warp walks as long as its longest line: 51 % lane
+// utilisation on lines of 8..120 bytes).  So a warp takes TWO tiles at a time, one per buffer, sorts each by
+// walk length (bitonic sort over shuffles), and lane k walks the k-th shortest line of the first tile followed
+// by the k-th longest of the second in ONE loop - the sums are nearly equal across lanes (82 %).  The copies
+// of a pair of tiles are not overlapped with its walk; the other warps of the SM cover them.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t l8_rslot(uint32_t c) { return (c ^ ((c >> 3) & 7)) << 4; }
+
+// ascending bitonic sort of one key per lane
+__device__ __forceinline__ uint32_t warp_sort32(uint32_t key, uint32_t lane) {
+#pragma unroll
+  for (uint32_t k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      const uint32_t other = __shfl_xor_sync(0xffffffffu, key, j);
+      const bool up = (lane & k) == 0;
+      const bool low = (lane & j) == 0;
+      key = (low == up) ? min(key, other) : max(key, other);
+    }
+  }
+  return key;
+}
 
 template <int CM>
 __device__ __forceinline__ void l8_run_ragged(const Lines8Params& p, const L8Ctx& cx, const uint32_t buf0, const uint32_t buf1,
@@ -909,7 +935,7 @@ __device__ __forceinline__ void l8_run_ragged(const Lines8Params& p, const L8Ctx
   constexpr uint32_t kCap = kL8WarpBuf - 16;  // the last 16 bytes stay free for the window that runs past the tile
 
   struct Plan {
-    uint32_t count;   // lines in the tile (0: the first line alone does not fit)
+    uint32_t count;   // lines in the tile (0: none left, or the first line alone does not fit)
     uint32_t start;   // this lane's line: first byte, relative to the tile buffer
     uint32_t len;     // this lane's line length in chars
   };
@@ -938,57 +964,92 @@ __device__ __forceinline__ void l8_run_ragged(const Lines8Params& p, const L8Ctx
         for (uint32_t j = lane; j < n_chunks; j += 32) cp_async16(buf + l8_rslot(j), src + (static_cast<uint64_t>(j) << 4));
       }
     }
-    cp_async_commit();
     return pl;
   };
 
   uint32_t c = lo;
-  uint32_t cur = buf0, nxt = buf1;
-  Plan pl = plan_and_stage(c, cur);
   while (c < hi) {
-    if (pl.count == 0) {  // a line longer than the buffer: walk it straight from global memory
-      cp_async_wait<0>();
+    const Plan pa = plan_and_stage(c, buf0);
+    if (pa.count == 0) {  // a line longer than the buffer: walk it straight from global memory
       if (lane == 0) l8_slow_line<CharT>(g, c);
       c += 1;
-      __syncwarp();
-      pl = plan_and_stage(c, cur);
       continue;
     }
-    const uint32_t c_next = c + pl.count;
-    const Plan pl_next = plan_and_stage(c_next, nxt);
-    cp_async_wait<1>();
+    const uint32_t cb = c + pa.count;
+    const Plan pb = plan_and_stage(cb, buf1);  // count 0: nothing left, or a long line that the next round handles
+    cp_async_commit();
+    // pair the lines: lane k gets rank k of tile A and rank 31 - k of tile B (keys: walk iterations, has-line, lane)
+    const bool own_a = lane < pa.count, own_b = lane < pb.count;
+    const uint32_t key_a = warp_sort32((own_a ? (pa.len + kPer - 1) / kPer : 0u) << 6 | (own_a ? 32u : 0u) | lane, lane);
+    const uint32_t key_b = __shfl_sync(0xffffffffu,
+                                       warp_sort32((own_b ? (pb.len + kPer - 1) / kPer : 0u) << 6 | (own_b ? 32u : 0u) | lane, lane), 31 - lane);
+    const bool has_a = (key_a & 32u) != 0, has_b = (key_b & 32u) != 0;
+    const uint32_t start_a = __shfl_sync(0xffffffffu, pa.start, key_a & 31u), len_a = __shfl_sync(0xffffffffu, pa.len, key_a & 31u);
+    const uint32_t start_b = __shfl_sync(0xffffffffu, pb.start, key_b & 31u), len_b = __shfl_sync(0xffffffffu, pb.len, key_b & 31u);
+    cp_async_wait<0>();
     __syncwarp();
 
-    if (lane < pl.count) {
-      const uint32_t len = pl.len;
-      const L8Align al(pl.start & 15u);
-      const uint32_t c0 = pl.start >> 4;
-      uint32_t e = cx.root;
-      int32_t last = g.fwd.root_accepting ? 0 : -1;
-      uint32_t tail_bit = g.fwd.root_accepting ? 1u : 0u;  // accept flag exactly at the end of the line (matches())
-      uint4 x = lds_data16(cur + l8_rslot(c0));
-      for (uint32_t pos = 0; pos < len; pos += kPer) {
-        const uint4 y = lds_data16(cur + l8_rslot(c0 + (pos / kPer) + 1));
-        const uint4 w = al.apply(x, y);
-        uint32_t mask = 0;
-        l8_chunk<CM>(w, p.q, cx, e, mask);
-        const uint32_t valid = min(kPer, len - pos);
-        mask >>= (kPer - valid);  // drop the accept bits of chars past the end of the line
-        const int32_t cand = static_cast<int32_t>(pos + valid + 1) - __ffs(mask);
-        last = mask ? cand : last;
-        tail_bit = mask & 1u;
-        x = y;
+    // one loop over both lines of the lane
+    uint32_t item = has_a ? 0u : has_b ? 1u : 2u;
+    uint32_t base = item == 0 ? buf0 : buf1;
+    uint32_t len = item == 0 ? len_a : len_b;
+    uint32_t start = item == 0 ? start_a : start_b;
+    L8Align al(start & 15u);
+    uint32_t c0 = start >> 4, pos = 0;
+    uint32_t e = cx.root;
+    const int32_t last0 = g.fwd.root_accepting ? 0 : -1;
+    const uint32_t tail0 = g.fwd.root_accepting ? 1u : 0u;  // accept flag exactly at the end of the line (matches())
+    int32_t last = last0, last_a = last0, last_b = last0;
+    uint32_t tail_bit = tail0, tail_a = tail0, tail_b = tail0;
+    uint4 x = make_uint4(0, 0, 0, 0);
+    if (item < 2) x = lds_data16(base + l8_rslot(c0));
+    while (__ballot_sync(0xffffffffu, item < 2) != 0) {
+      if (item < 2) {
+        if (pos < len) {
+          const uint4 y = lds_data16(base + l8_rslot(c0 + (pos / kPer) + 1));
+          const uint4 w = al.apply(x, y);
+          uint32_t mask = 0;
+          l8_chunk<CM>(w, p.q, cx, e, mask);
+          const uint32_t valid = min(kPer, len - pos);
+          mask >>= (kPer - valid);  // drop the accept bits of chars past the end of the line
+          const int32_t cand = static_cast<int32_t>(pos + valid + 1) - __ffs(mask);
+          last = mask ? cand : last;
+          tail_bit = mask & 1u;
+          x = y;
+          pos += kPer;
+          // a dead automaton stays dead (and never accepts): the rest of the line cannot change the result
+          if ((e & L8Enc<CM>::kStateMask) == cx.fwd_dead) pos = len;
+        }
+        if (pos >= len) {  // this line is done: keep its result, move on to the lane's second line
+          if (item == 0) {
+            last_a = last;
+            tail_a = tail_bit;
+          } else {
+            last_b = last;
+            tail_b = tail_bit;
+          }
+          item = (item == 0 && has_b) ? 1u : 2u;
+          if (item == 1) {
+            base = buf1;
+            len = len_b;
+            al = L8Align(start_b & 15u);
+            c0 = start_b >> 4;
+            pos = 0;
+            e = cx.root;
+            last = last0;
+            tail_bit = tail0;
+            x = lds_data16(base + l8_rslot(c0));
+          }
+        }
       }
-      l8_finish<CM, CharT>(p, cx, c + lane, len, last, tail_bit != 0, pl.start, [&](uint32_t ch) { return cur + l8_rslot(ch); });
     }
-    __syncwarp();
-    c = c_next;
-    pl = pl_next;
-    const uint32_t tmp = cur;
-    cur = nxt;
-    nxt = tmp;
+    if (has_a)
+      l8_finish<CM, CharT>(p, cx, c + (key_a & 31u), len_a, last_a, tail_a != 0, start_a, [&](uint32_t ch) { return buf0 + l8_rslot(ch); });
+    if (has_b)
+      l8_finish<CM, CharT>(p, cx, cb + (key_b & 31u), len_b, last_b, tail_b != 0, start_b, [&](uint32_t ch) { return buf1 + l8_rslot(ch); });
+    __syncwarp();  // every lane is done with both buffers before the next pair of tiles overwrites them
+    c = cb + pb.count;
   }
-  cp_async_wait<0>();
 }
 
 template <int CM>
@@ -1091,6 +1152,7 @@ __global__ void __launch_bounds__(kL8Threads, 1) lines8_kernel(const Lines8Param
   cx.root = p.root_entry;
   cx.bwd_root = p.bwd_root;
   cx.bwd_dead = p.bwd_dead;
+  cx.fwd_dead = p.fwd_dead;
   if (p.char_mode == kCmBytes1) l8_dispatch<kCmBytes1>(p, cx, log2cpl, buf0, buf1, lane, warp_global, n_warps);
   else if (p.char_mode == kCmBytes) l8_dispatch<kCmBytes>(p, cx, log2cpl, buf0, buf1, lane, warp_global, n_warps);
   else if (p.char_mode == kCmHi) l8_dispatch<kCmHi>(p, cx, log2cpl, buf0, buf1, lane, warp_global, n_warps);
@@ -1150,6 +1212,7 @@ __global__ void __launch_bounds__(kQThreads, 1) linesq_kernel(const Lines8Params
   cx.root = p.root_entry + lane_off;
   cx.bwd_root = p.bwd_root + lane_off;
   cx.bwd_dead = p.bwd_dead + lane_off;
+  cx.fwd_dead = p.fwd_dead + lane_off;
   l8_dispatch<CM>(p, cx, log2cpl, buf0, buf1, lane, blockIdx.x * usable_warps + warp, gridDim.x * usable_warps);
 }
 
