@@ -50,6 +50,35 @@ public final class GpuPattern implements Pattern, AutoCloseable {
         return r;
     }
 
+    /** All non-overlapping matches of every haystack (CSR): {@code while (m.find())} per haystack, in two passes. */
+    public static final class AllMatches {
+        public int[] counts;
+        public long[] matchOffsets;
+        public int[] starts;
+        public int[] ends;
+    }
+
+    public AllMatches findAllBatch(ByteBuffer data, ByteBuffer offsets, int n, int charWidth) {
+        AllMatches r = new AllMatches();
+        r.counts = new int[n];
+        ByteBuffer off = offsets.order(ByteOrder.LITTLE_ENDIAN);
+        NeedleNative.findAllBatch(handle, data, off, n, charWidth, r.counts, null, null, null);
+        r.matchOffsets = new long[n + 1];
+        ByteBuffer mo = ByteBuffer.allocateDirect(8 * (n + 1)).order(ByteOrder.LITTLE_ENDIAN);
+        long total = 0;
+        for (int i = 0; i < n; i++) {
+            mo.putLong(8 * i, total);
+            r.matchOffsets[i] = total;
+            total += r.counts[i] & 0xffffffffL;
+        }
+        mo.putLong(8 * n, total);
+        r.matchOffsets[n] = total;
+        r.starts = new int[(int) total];
+        r.ends = new int[(int) total];
+        NeedleNative.findAllBatch(handle, data, off, n, charWidth, r.counts, mo, r.starts, r.ends);
+        return r;
+    }
+
     /** Convenience: find() on every string. */
     public BatchResult findAll(String[] haystacks) {
         return NeedleNative.findAllStrings(handle, haystacks);

@@ -26,6 +26,14 @@ final class NeedleNative {
     /** One string through ndl_match_batch (GetStringCritical -> UTF-16 code units, char_width 2). Returns {matched, start, end}. */
     static native int[] matchOne(long handle, int mode, String s, int from);
 
+    /**
+     * ndl_find_all_batch with NDL_MEM_HOST on direct buffers: the loop {@code while (m.find())} for every haystack.
+     * Pass 1: {@code matchOffsets == null} fills {@code counts}; pass 2: {@code matchOffsets} = exclusive prefix sum
+     * (n + 1 longs, little endian), {@code starts}/{@code ends} sized to its last element.
+     */
+    static native void findAllBatch(long handle, ByteBuffer data, ByteBuffer offsets, int n, int charWidth, int[] counts,
+                                    ByteBuffer matchOffsets, int[] starts, int[] ends);
+
     /** Packs the strings with GetStringRegion into one pinned staging buffer and runs find() on all of them. */
     static native GpuPattern.BatchResult findAllStrings(long handle, String[] haystacks);
 }

@@ -71,6 +71,24 @@ JNIEXPORT void JNICALL Java_com_justinblank_strings_gpu_NeedleNative_matchBatch(
   if (rc != NDL_OK) throw_for(env, rc);
 }
 
+JNIEXPORT void JNICALL Java_com_justinblank_strings_gpu_NeedleNative_findAllBatch(JNIEnv* env, jclass k, jlong h, jobject data, jobject offsets,
+                                                                                  jint n, jint charWidth, jintArray counts,
+                                                                                  jobject matchOffsets, jintArray starts, jintArray ends) {
+  (void)k;
+  const void* d = (*env)->GetDirectBufferAddress(env, data);
+  const uint64_t* o = (const uint64_t*)(*env)->GetDirectBufferAddress(env, offsets);
+  const uint64_t* mo = matchOffsets ? (const uint64_t*)(*env)->GetDirectBufferAddress(env, matchOffsets) : NULL;
+  jint* c = (*env)->GetPrimitiveArrayCritical(env, counts, NULL);
+  jint* s = mo ? (*env)->GetPrimitiveArrayCritical(env, starts, NULL) : NULL;
+  jint* e = mo ? (*env)->GetPrimitiveArrayCritical(env, ends, NULL) : NULL;
+  int rc = ndl_find_all_batch((ndl_pattern*)(intptr_t)h, d, o, (uint64_t)n, charWidth, (uint32_t*)c, mo, (int32_t*)s, (int32_t*)e,
+                              NDL_MEM_HOST, NULL);
+  if (e) (*env)->ReleasePrimitiveArrayCritical(env, ends, e, 0);
+  if (s) (*env)->ReleasePrimitiveArrayCritical(env, starts, s, 0);
+  (*env)->ReleasePrimitiveArrayCritical(env, counts, c, 0);
+  if (rc != NDL_OK) throw_for(env, rc);
+}
+
 JNIEXPORT jintArray JNICALL Java_com_justinblank_strings_gpu_NeedleNative_matchOne(JNIEnv* env, jclass k, jlong h, jint mode, jstring s, jint from) {
   (void)k;
   jsize n = (*env)->GetStringLength(env, s);

@@ -591,6 +591,91 @@ int ndl_match_batch(ndl_pattern* p, int mode, const void* data, const uint64_t* 
   return NDL_OK;
 }
 
+
+int ndl_find_all_batch(ndl_pattern* p, const void* data, const uint64_t* offsets, uint64_t n, int char_width, uint32_t* counts,
+                       const uint64_t* match_offsets, int32_t* starts, int32_t* ends, int mem_kind, void* stream_) {
+  if (!p) return fail(NDL_EINVAL, "pattern must not be NULL");
+  if (char_width != 1 && char_width != 2) return fail(NDL_EINVAL, "char_width must be 1 or 2");
+  if (mem_kind != NDL_MEM_HOST && mem_kind != NDL_MEM_DEVICE) return fail(NDL_EINVAL, "mem_kind must be NDL_MEM_HOST or NDL_MEM_DEVICE");
+  if (n == 0) return NDL_OK;
+  if (!offsets || !counts) return fail(NDL_EINVAL, "offsets and counts must not be NULL");
+  if (match_offsets && (!starts || !ends)) return fail(NDL_EINVAL, "starts and ends are required with match_offsets");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NDL_CUDA(cudaSetDevice(p->device));
+  FindAllParams q;
+  std::memset(&q, 0, sizeof(q));
+  q.b.n = n;
+  q.b.mode = NDL_MODE_FIND;
+  q.b.min_length = p->cp.min_length;
+  q.b.max_length = p->cp.max_length;
+  q.b.reverse_mode = p->cp.reverse_mode;
+  q.b.reverse_char = p->cp.reverse_char;
+  q.b.fwd = p->tables[kForwards].view();
+  q.b.bwd = p->tables[kBackwards].view();
+  auto launch = [&]() -> int {
+    const int threads = 256;
+    const uint64_t want = (n + threads - 1) / threads, max_blocks = static_cast<uint64_t>(p->sm_count) * 32;
+    const int blocks = static_cast<int>(want < max_blocks ? want : max_blocks);
+    if (char_width == 1)
+      find_all_kernel<uint8_t><<<blocks, threads, 0, stream>>>(q);
+    else
+      find_all_kernel<uint16_t><<<blocks, threads, 0, stream>>>(q);
+    g_launches.fetch_add(1);
+    NDL_CUDA(cudaGetLastError());
+    return NDL_OK;
+  };
+  if (mem_kind == NDL_MEM_DEVICE) {
+    q.b.data = data;
+    q.b.offsets = offsets;
+    q.counts = counts;
+    q.match_offsets = match_offsets;
+    q.starts = starts;
+    q.ends = ends;
+    return launch();
+  }
+  // host buffers: stage in, launch, stage out on `stream`, then wait
+  if (offsets[0] > offsets[n]) return fail(NDL_EINVAL, "offsets must be non-decreasing");
+  const uint64_t base = offsets[0];
+  const size_t data_bytes = static_cast<size_t>(offsets[n] - base) * char_width;
+  const uint64_t total = match_offsets ? match_offsets[n] - match_offsets[0] : 0;
+  std::lock_guard<std::mutex> lock(p->ws_mutex);
+  Workspace& ws = p->ws;
+  int rc = ensure_workspace(ws, data_bytes + 64, n, false, true);
+  if (rc != NDL_OK) return rc;
+  uint32_t* d_counts = nullptr;
+  uint64_t* d_moff = nullptr;
+  int32_t *d_starts = nullptr, *d_ends = nullptr;
+  struct Guard { void *a, *b, *c, *d; ~Guard() { cudaFree(a); cudaFree(b); cudaFree(c); cudaFree(d); } } guard{nullptr, nullptr, nullptr, nullptr};
+  NDL_CUDA(cudaMalloc(&d_counts, n * sizeof(uint32_t)));
+  guard.a = d_counts;
+  if (match_offsets) {
+    NDL_CUDA(cudaMalloc(&d_moff, (n + 1) * sizeof(uint64_t)));
+    guard.b = d_moff;
+    NDL_CUDA(cudaMalloc(&d_starts, (total + 1) * sizeof(int32_t)));
+    guard.c = d_starts;
+    NDL_CUDA(cudaMalloc(&d_ends, (total + 1) * sizeof(int32_t)));
+    guard.d = d_ends;
+    NDL_CUDA(cudaMemcpyAsync(d_moff, match_offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+  }
+  NDL_CUDA(cudaMemcpyAsync(ws.offsets, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+  if (data_bytes)
+    NDL_CUDA(cudaMemcpyAsync(ws.data, static_cast<const uint8_t*>(data) + base * char_width, data_bytes, cudaMemcpyHostToDevice, stream));
+  q.b.data = static_cast<const uint8_t*>(ws.data) - base * char_width;
+  q.b.offsets = ws.offsets;
+  q.counts = d_counts;
+  q.match_offsets = d_moff;
+  // the device arrays start at match 0 of this call
+  q.starts = d_starts ? d_starts - match_offsets[0] : nullptr;
+  q.ends = d_ends ? d_ends - match_offsets[0] : nullptr;
+  if ((rc = launch()) != NDL_OK) return rc;
+  NDL_CUDA(cudaMemcpyAsync(counts, d_counts, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+  if (match_offsets && total) {
+    NDL_CUDA(cudaMemcpyAsync(starts + match_offsets[0], d_starts, total * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    NDL_CUDA(cudaMemcpyAsync(ends + match_offsets[0], d_ends, total * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  }
+  NDL_CUDA(cudaStreamSynchronize(stream));
+  return NDL_OK;
+}
 }  // extern "C"
 
 static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, int char_width, int64_t from, int32_t entry_state,

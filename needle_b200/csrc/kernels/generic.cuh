@@ -119,4 +119,50 @@ __global__ void __launch_bounds__(256) generic_batch_kernel(const BatchParams p)
   }
 }
 
+// All non-overlapping matches of every haystack: the loop `while (m.find()) { m.start(); m.end(); }` of
+// DFACompilerTest.java:678-699.  find() resumes at nextStart = end of the previous match
+// (DFAClassBuilder.java:634-635) and its reverse pass is bounded below by that index (:640-659).  A match
+// that does not move nextStart forward (an empty match) would be reported forever by the
+// reference: here it is reported once and ends the loop, so `from` strictly increases and the loop terminates.
+// counts[i] = number of matches; when match_offsets != NULL, match k of haystack i is stored at
+// match_offsets[i] + k as long as that is below match_offsets[i + 1] (two-pass CSR: count, scan, fill).
+struct FindAllParams {
+  BatchParams b;                  // data, offsets, n, tables, reverse mode (matched/start/end/from unused)
+  uint32_t* counts;
+  const uint64_t* match_offsets;  // nullable
+  int32_t* starts;
+  int32_t* ends;
+};
+
+template <typename CharT>
+__global__ void __launch_bounds__(256) find_all_kernel(const FindAllParams q) {
+  const BatchParams& p = q.b;
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.n; i += stride) {
+    const uint64_t o0 = p.offsets[i], o1 = p.offsets[i + 1];
+    const CharT* s = static_cast<const CharT*>(p.data) + o0;
+    const int64_t len = static_cast<int64_t>(o1 - o0);
+    uint64_t out = 0, cap = 0;
+    if (q.match_offsets) {
+      out = q.match_offsets[i];
+      cap = q.match_offsets[i + 1] - out;
+    }
+    uint32_t count = 0;
+    int64_t from = 0;
+    for (;;) {
+      const int64_t e = dev_index_forwards<CharT>(p, s, len, from);
+      if (e == -1) break;
+      const int64_t st = (p.reverse_mode == 2) ? e - p.min_length : dev_index_backwards<CharT>(p, s, e - 1, from, 0x7fffffff);
+      if (count < cap) {
+        q.starts[out + count] = static_cast<int32_t>(st);
+        q.ends[out + count] = static_cast<int32_t>(e);
+      }
+      count++;
+      if (e <= from) break;  // nextStart did not advance: the reference would repeat this match forever
+      from = e;
+    }
+    q.counts[i] = count;
+  }
+}
+
 }  // namespace ndl

@@ -196,6 +196,32 @@ class Pattern:
         if rc != _lib.NDL_OK:
             _raise(rc, "ndl_match_batch")
 
+    def find_all_batch(self, data: np.ndarray, offsets: np.ndarray, char_width: int = 1):
+        """All non-overlapping matches of every haystack (`while (m.find())`, DFACompilerTest.java:678-699) from HOST
+        buffers, as CSR: returns (counts uint32[n], match_offsets uint64[n+1], starts int32[total], ends int32[total]).
+        Two passes through `ndl_find_all_batch`: count, prefix sum on the host, fill."""
+        n = len(offsets) - 1
+        data = np.ascontiguousarray(data).view(np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        counts = np.zeros(n, dtype=np.uint32)
+        moff = np.zeros(n + 1, dtype=np.uint64)
+        if n == 0:
+            return counts, moff, np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32)
+        L = _lib.lib()
+        rc = L.ndl_find_all_batch(self._h, data.ctypes.data if data.size else None, offsets.ctypes.data, n, char_width,
+                                  counts.ctypes.data, None, None, None, _lib.MEM_HOST, None)
+        if rc != _lib.NDL_OK:
+            _raise(rc, "ndl_find_all_batch")
+        moff[1:] = np.cumsum(counts, dtype=np.uint64)
+        total = int(moff[-1])
+        starts = np.full(max(total, 1), -1, dtype=np.int32)
+        ends = np.full(max(total, 1), -1, dtype=np.int32)
+        rc = L.ndl_find_all_batch(self._h, data.ctypes.data if data.size else None, offsets.ctypes.data, n, char_width,
+                                  counts.ctypes.data, moff.ctypes.data, starts.ctypes.data, ends.ctypes.data, _lib.MEM_HOST, None)
+        if rc != _lib.NDL_OK:
+            _raise(rc, "ndl_find_all_batch")
+        return counts, moff, starts[:total], ends[:total]
+
     def find_long(self, data: np.ndarray, from_: int = 0, char_width: int = 1):
         """find() over ONE haystack of any length (64-bit offsets; BASELINE config 4) from a HOST array.
         Returns (matched, start, end)."""
@@ -368,10 +394,9 @@ class Precompile:
 def iter_find(pattern: Pattern, s: str) -> Iterable[Tuple[int, int]]:
     """while (m.find()) yield (m.start(), m.end()) - the loop of DFACompilerTest.java:678-699."""
     m = pattern.matcher(s)
-    prev = None
+    nxt = 0
     while m.find():
-        cur = (m.start(), m.end())
-        if cur == prev:  # an empty match repeats forever in the reference (nextStart == end); stop instead
+        yield (m.start(), m.end())
+        if m.end() <= nxt:  # nextStart did not advance (empty match): the reference would repeat it forever; stop instead
             break
-        yield cur
-        prev = cur
+        nxt = m.end()

@@ -109,15 +109,45 @@ class Oracle:
         return bool(m), st.value, en.value
 
     def find_iter(self, s):
-        """All successive find() results on one Matcher (nextStart = end), stopping on a repeated empty match."""
-        out, frm, prev = [], 0, None
-        while frm != -1:
+        """All successive find() results on one Matcher (nextStart = end).  A match that does not move nextStart forward
+        (an empty match) would repeat forever in the reference: it is reported once and ends the list."""
+        out, frm = [], 0
+        while True:
             m, st, en = self.find(s, frm)
-            if not m or (st, en) == prev:
+            if not m:
                 break
             out.append((st, en))
-            prev, frm = (st, en), en
+            if en <= frm:
+                break
+            frm = en
         return out
+
+    def find_all_batch(self, data, offsets, char_width=1, threads=1):
+        """find_iter over a batch, as CSR (counts, match_offsets, starts, ends): rounds of ndlo_match_batch with `from` offsets."""
+        n = len(offsets) - 1
+        frm = np.zeros(n, dtype=np.int32)
+        active = np.ones(n, dtype=bool)
+        rounds = []
+        while active.any():
+            m, s, e = self.match_batch(2, data, offsets, char_width, frm, threads)
+            hit = active & (m == 1)
+            rounds.append((np.nonzero(hit)[0], s[hit].copy(), e[hit].copy()))
+            adv = hit & (e > frm)
+            frm = np.where(adv, e, frm).astype(np.int32)
+            active = adv
+        counts = np.zeros(n, dtype=np.uint32)
+        for idx, _, _ in rounds:
+            counts[idx] += 1
+        moff = np.zeros(n + 1, dtype=np.uint64)
+        moff[1:] = np.cumsum(counts, dtype=np.uint64)
+        starts = np.zeros(int(moff[-1]), dtype=np.int32)
+        ends = np.zeros(int(moff[-1]), dtype=np.int32)
+        fill = moff[:-1].astype(np.int64).copy()
+        for idx, s, e in rounds:
+            starts[fill[idx]] = s
+            ends[fill[idx]] = e
+            fill[idx] += 1
+        return counts, moff, starts, ends
 
     def scan_from(self, data, entry_state=0, last_init=-1, from_=0, cw=1):
         """(last, exit_state) of the forward scan of a chunk from an arbitrary state (multi-rank protocol check)."""

@@ -301,6 +301,56 @@ def test_utf16_ragged_and_unsupported_class_maps():
         assert_batch_equal(regex, fl, data, offsets, cw)
 
 
+FIND_ALL_CASES = [
+    (workloads.REGEX["c2"], b"0123456789-- x", 1),
+    (workloads.REGEX["c3"], b"abc019._%+-@@ ,;", 1),
+    (r"[0-9]+", b"0123456789ab ", 1),
+    (r"a*", b"aab", 1),             # empty matches: reported once, then the haystack's list ends
+    (r"a|b*", b"ab c", 1),
+    (r"(ab|a|b-)+", b"ab- ", 1),
+    (workloads.REGEX["c5"], None, 2),
+]
+
+
+@pytest.mark.parametrize("regex,alphabet,cw", FIND_ALL_CASES, ids=[c[0][:16] for c in FIND_ALL_CASES])
+def test_find_all_batch_matches_the_iterated_find_of_the_oracle(regex, alphabet, cw):
+    """ndl_find_all_batch: `while (m.find())` per haystack, CSR output, against the oracle's find(from) loop."""
+    rng = np.random.default_rng(len(regex))
+    n = 3000
+    lens = rng.integers(0, 90, size=n)
+    offsets = np.zeros(n + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum(lens)
+    total = int(offsets[-1])
+    if cw == 1:
+        a = np.frombuffer(alphabet, dtype=np.uint8)
+        data = a[rng.integers(0, len(a), size=total)].copy()
+    else:
+        chars = rng.integers(0x5F0, 0x710, size=total).astype(np.uint16)
+        chars[rng.random(total) < 0.4] = 0x20
+        data = chars.view(np.uint8)
+    pat, ora = pair(regex)
+    got = pat.find_all_batch(data, offsets, cw)
+    exp = ora.find_all_batch(data, offsets, cw, threads=8)
+    for name, g, e in zip(("counts", "match_offsets", "starts", "ends"), got, exp):
+        assert np.array_equal(g, e), (regex, name, g[:10], e[:10])
+    assert int(got[0].sum()) > 0
+    # the per-string loop of the Python mirror agrees on a few haystacks
+    for i in range(0, 60, 7):
+        o0, o1 = int(offsets[i]), int(offsets[i + 1])
+        hay = bytes(data[o0 * cw:o1 * cw]).decode("latin-1" if cw == 1 else "utf-16-le")
+        k0, k1 = int(got[1][i]), int(got[1][i + 1])
+        assert list(nb.iter_find(pat, hay)) == list(zip(got[2][k0:k1].tolist(), got[3][k0:k1].tolist())) == ora.find_iter(hay)
+
+
+def test_find_all_batch_count_only_and_short_capacity():
+    pat, ora = pair(r"[0-9]+")
+    data = np.frombuffer(b"1 22 333 4444" + b"no digits" + b"7", dtype=np.uint8)
+    offsets = np.array([0, 13, 22, 23], dtype=np.uint64)
+    counts, moff, starts, ends = pat.find_all_batch(data, offsets, 1)
+    assert counts.tolist() == [4, 0, 1] and moff.tolist() == [0, 4, 4, 5]
+    assert list(zip(starts.tolist(), ends.tolist())) == [(0, 1), (2, 4), (5, 8), (9, 13), (0, 1)]
+
+
 def fast_path(pat, mode, cw):
     L = _lib.lib()
     L.ndl_debug_fast_path.argtypes = [__import__("ctypes").c_void_p, __import__("ctypes").c_int, __import__("ctypes").c_int]
