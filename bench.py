@@ -40,6 +40,7 @@ WORKLOADS = {
     "c4b": ("c4", "BASELINE configs[3] batched variant: 256-state DFA 'a[ab]{7}c' find() over 64-byte lines of {a,b}", workloads.c4_lines, 10_000_000, 1),
     "c3": ("c3", "BASELINE configs[2]: email-like regex find() over mixed-length lines (8..120 B)", workloads.c3_lines, 10_000_000, 1),
     "c5": ("c5", "BASELINE configs[4]: BMP char-class regex find() over UTF-16LE lines of 32 chars (64 B)", workloads.c5_lines, 10_000_000, 2),
+    "c2w": ("c2", "BASELINE configs[1] regex over UTF-16LE lines of 32 chars (64 B), i.e. java.lang.String payloads", workloads.c2_lines_utf16, 10_000_000, 2),
     # the configuration of BASELINE.json's target sentence: 8 GiB of batched haystacks, 256-state DFA
     "c4b8g": ("c4", "BASELINE north-star target: 256-state DFA 'a[ab]{7}c' find() over 8 GiB of batched 64-byte lines of {a,b} (2^27 lines)", workloads.c4_lines, 1 << 27, 1),
 }
@@ -381,14 +382,29 @@ def run_long(args, rank, local_rank, world):
     # end to end from pinned host memory on a (at most) 1 GiB buffer per rank (same content law)
     ne = min(n, 1 << 30)
     e2e_steps, e2e_s = 3, None
+    host = data[n - ne:].cpu().pin_memory()
     if world == 1:
-        host = data[n - ne:].cpu().pin_memory()
-        pat.find_long_ptrs(host.data_ptr(), ne, 1, 0, nb.MEM_HOST, stream.cuda_stream)
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            r = pat.find_long_ptrs(host.data_ptr(), ne, 1, 0, nb.MEM_HOST, stream.cuda_stream)
-        e2e_s = time.perf_counter() - t0
-        assert r == (True, ne - 9, ne)
+        def step_host():
+            return pat.find_long_ptrs(host.data_ptr(), ne, 1, 0, nb.MEM_HOST, stream.cuda_stream)
+    else:
+        def step_host():  # the same protocol over host-resident chunks of ne bytes per rank
+            return sharding.find_long_sharded(
+                lambda entry: pat.find_long_from(host.data_ptr(), ne, entry, mem_kind=nb.MEM_HOST, stream=stream.cuda_stream),
+                lambda index, entry, li: pat.find_long_back(host.data_ptr(), ne, index, entry, li, mem_kind=nb.MEM_HOST, stream=stream.cuda_stream),
+                lambda: pat.find_long_from(halo.ctypes.data, halo.size, 0, mem_kind=nb.MEM_HOST, stream=stream.cuda_stream)[1],
+                rank * ne, ne, rank, world, allgather, fd, bd, pat.reverse_mode, pat.min_length, pat.backwards_root_accepting)
+    step_host()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        r = step_host()
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    assert r == (True, world * ne - 9, world * ne), r
+    if dist:
+        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.item())
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
     if dist:
@@ -412,8 +428,9 @@ def run_long(args, rank, local_rank, world):
                          "algorithmic_bytes_per_launch": n},
         }
         if e2e_s is not None:
-            line["e2e"] = {"value": ne * e2e_steps / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": ne, "d2h_bytes_per_step": 17,
-                           "steps": e2e_steps, "note": f"host path measured on a {ne >> 20} MiB haystack"}
+            line["e2e"] = {"value": world * ne * e2e_steps / e2e_s / 1e9, "unit": UNIT, "h2d_bytes_per_step": world * ne,
+                           "d2h_bytes_per_step": 17 * world, "steps": e2e_steps,
+                           "note": f"host path measured on a {ne >> 20} MiB haystack per rank"}
         print(json.dumps(line), flush=True)
     if dist:
         dist.destroy_process_group()

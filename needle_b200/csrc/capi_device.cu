@@ -166,6 +166,9 @@ static LinesqKernel linesq_kernel_for(int cm) {
 #define NDL_Q16(pl) case cm_swar(2, pl, false, true): return linesq_kernel<cm_swar(2, pl, false, true)>;
     NDL_Q16(1) NDL_Q16(2) NDL_Q16(3)
 #undef NDL_Q16
+#define NDL_QW(k, pl) case cm_swar_wide(k, pl): return linesq_kernel<cm_swar_wide(k, pl)>;
+    NDL_QW(4, 1) NDL_QW(4, 2) NDL_QW(4, 3) NDL_QW(2, 1) NDL_QW(2, 2) NDL_QW(2, 3)
+#undef NDL_QW
     default: return nullptr;
   }
 }
@@ -307,15 +310,14 @@ int ndl_debug_swar_emulate(const uint8_t* blob, size_t blob_len, int mode, int c
     info[3] = static_cast<int32_t>(img.size());
   }
   const int K = cm_k(b.char_mode), P = cm_planes(b.char_mode);
-  const bool u16 = cm_u16(b.char_mode);
+  const bool u16 = cm_u16(b.char_mode), wide = cm_wide(b.char_mode);
   const uint32_t state_mask = u16 ? 0x3fffu : 0xffffffffu >> K;
   const uint32_t lane_off = (static_cast<uint32_t>(lane) & b.q.copy_mask) * b.q.copy_bytes;
   const HostDeviceTable& t = backward ? bt : f;
-  auto slot_at = [&](uint64_t i) -> uint32_t {  // slot value of char i (0 past the end)
-    if (i >= n_chars) return 0;
-    return char_width == 1 ? data[i] : data[2 * i + 1];
-  };
   auto char_at = [&](uint64_t i) -> uint32_t { return char_width == 1 ? data[i] : (data[2 * i] | data[2 * i + 1] << 8); };
+  auto slot_at = [&](uint64_t i) -> uint32_t {  // slot value of char i
+    return char_width == 1 ? data[i] : wide ? char_at(i) : data[2 * i + 1];
+  };
   auto dp4a = [](uint32_t a, uint32_t w, uint32_t c) {
     for (int i = 0; i < 4; i++) c += ((a >> (8 * i)) & 0xff) * ((w >> (8 * i)) & 0xff);
     return c;
@@ -326,35 +328,48 @@ int ndl_debug_swar_emulate(const uint8_t* blob, size_t blob_len, int mode, int c
     std::memcpy(&v, img.data() + (addr - kQAbsTrans), u16 ? 2 : 4);
     return u16 ? v << 16 | v : v;  // 16-bit entry: flags seen in the top bits, row address in the low 14
   };
+  const uint32_t top = wide ? 0x80008000u : 0x80808080u;
+  auto planes_dp = [&](uint32_t w, int widx, uint32_t acc) {  // compare planes of one word -> IDP.4A with weight set widx
+    const uint32_t w80 = w | top, nm = ~w & top;
+    for (int p = 0; p < P; p++) acc = dp4a(((w80 - b.q.lo[p]) ^ (w80 - b.q.hi[p])) & nm, b.q.w[p][widx], acc);
+    return acc;
+  };
   int diffs = 0;
   uint32_t e = (backward ? b.bwd_root : b.root_entry) + lane_off;
   int st = 0;
   const uint64_t groups = (n_chars + 3) / 4;
   for (uint64_t gi = 0; gi < groups; gi++) {
-    // word of four slot values in walk order: forwards chars 4g..4g+3 sit in bytes 0..3; backwards the walk
-    // starts at the last char, and the kernel's reverse step reads byte 3 first
-    uint32_t w = 0;
+    // four slot values in walk order (backwards: from the last char down); past the ends: 0
     uint64_t idx[4];
+    uint32_t c[4];
     for (int j = 0; j < 4; j++) {
-      idx[j] = backward ? n_chars - 1 - (4 * gi + j) : 4 * gi + j;  // j-th char walked (may wrap past 0: then >= n_chars)
-      const uint32_t sv = idx[j] < n_chars ? slot_at(idx[j]) : 0;
-      w |= sv << (8 * (backward ? 3 - j : j));
+      idx[j] = backward ? n_chars - 1 - (4 * gi + j) : 4 * gi + j;  // (wraps past 0: then >= n_chars)
+      c[j] = idx[j] < n_chars ? slot_at(idx[j]) : 0;
     }
-    const uint32_t w80 = w | 0x80808080u, nm = ~w & 0x80808080u;
-    uint32_t pl[3] = {0, 0, 0};
-    for (int p = 0; p < P; p++) pl[p] = ((w80 - b.q.lo[p]) ^ (w80 - b.q.hi[p])) & nm;
+    uint32_t da, db;  // column offsets of the first / second pair (K = 4: da is the whole group's)
+    const int w_first = backward ? 2 : 0;
+    if (wide) {
+      // a word holds two chars; walking backwards the char walked first sits in the high half
+      const uint32_t wa = backward ? (c[1] | c[0] << 16) : (c[0] | c[1] << 16);
+      const uint32_t wb = backward ? (c[3] | c[2] << 16) : (c[2] | c[3] << 16);
+      if (K == 4) {
+        da = planes_dp(wb, backward ? 3 : 1, planes_dp(wa, w_first, 0));
+        db = 0;
+      } else {
+        da = planes_dp(wa, w_first, 0);
+        db = planes_dp(wb, w_first, 0);
+      }
+    } else {
+      uint32_t w = 0;  // forwards char j sits in byte j; the kernel's reverse step reads byte 3 first
+      for (int j = 0; j < 4; j++) w |= c[j] << (8 * (backward ? 3 - j : j));
+      da = planes_dp(w, w_first, 0);
+      db = K == 4 ? 0 : planes_dp(w, backward ? 3 : 1, 0);
+    }
     uint32_t flags4 = 0;
     if (K == 4) {
-      uint32_t dp = 0;
-      for (int p = 0; p < P; p++) dp = dp4a(pl[p], b.q.w[p][backward ? 2 : 0], dp);
-      e = lds(dp * b.q.kmul + (e & state_mask));
+      e = lds(da * b.q.kmul + (e & state_mask));
       flags4 = e >> 28;
     } else {
-      uint32_t da = 0, db = 0;
-      for (int p = 0; p < P; p++) {
-        da = dp4a(pl[p], b.q.w[p][backward ? 2 : 0], da);
-        db = dp4a(pl[p], b.q.w[p][backward ? 3 : 1], db);
-      }
       e = lds(da * b.q.kmul + (e & state_mask));
       flags4 = (e >> 30) << 2;
       e = lds(db * b.q.kmul + (e & state_mask));
@@ -385,7 +400,8 @@ const char* ndl_debug_kernel_name(const ndl_pattern* p, int mode, int char_width
   const Lines8Blob& lb = char_width == 1 ? p->l8[mode] : p->l16[mode];
   if (qb.ok) {
     name = "linesq_kernel<" + std::to_string(cm_k(qb.char_mode)) + " chars/lookup, " + std::to_string(cm_planes(qb.char_mode)) +
-           " compare planes, " + std::to_string(qb.replicated) + (cm_u16(qb.char_mode) ? " table copies of 16-bit entries" : " table copies") + (cm_hi(qb.char_mode) ? ", UTF-16 high byte>" : ">");
+           " compare planes, " + std::to_string(qb.replicated) + (cm_u16(qb.char_mode) ? " table copies of 16-bit entries" : " table copies") +
+           (cm_wide(qb.char_mode) ? ", UTF-16 on 16-bit lanes>" : cm_hi(qb.char_mode) ? ", UTF-16 high byte>" : ">");
   } else if (lb.ok) {
     static const char* kModes[] = {"pair table", "UTF-16 high byte", "UTF-16 mixed page", "stride-1 table"};
     name = std::string("lines8_kernel<") + kModes[lb.char_mode & 3] + ">";

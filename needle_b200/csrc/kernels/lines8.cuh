@@ -89,6 +89,8 @@ enum { kCmBytes = 0, kCmHi = 1, kCmMixed = 2, kCmBytes1 = 3 };
 // the column offset of a K-char group is a dot product (IDP.4A) of the compare planes with per-position
 // weights.  Encoded as 16 | u16 << 5 | (K == 4) << 3 | hi << 2 | planes:
 //   u16 = 1 16-bit table entries (K = 2 only): twice the copies in the same space, see linesq_layout
+//   wide (bit 6) char_width 2 with the compares done on 16-bit lanes (thresholds up to 0x8000, chars above share one
+//           class): two chars per word, e.g. an ASCII pattern over UTF-16 text - a java.lang.String
 //   hi = 0  char_width 1, four chars per word
 //   hi = 1  char_width 2 with the class decided by the HIGH byte of a char (as kCmHi): the high bytes of
 //           two words are gathered into one (PRMT) and then classified like bytes
@@ -96,6 +98,8 @@ __host__ __device__ constexpr int cm_swar(int k, int planes, bool hi, bool u16 =
   return 16 | (u16 ? 32 : 0) | (k == 4 ? 8 : 0) | (hi ? 4 : 0) | planes;
 }
 __host__ __device__ constexpr bool cm_u16(int cm) { return cm >= 16 && (cm & 32) != 0; }
+__host__ __device__ constexpr int cm_swar_wide(int k, int planes) { return 64 | 16 | (k == 4 ? 8 : 0) | planes; }
+__host__ __device__ constexpr bool cm_wide(int cm) { return cm >= 16 && (cm & 64) != 0; }
 __host__ __device__ constexpr bool cm_is_swar(int cm) { return cm >= 16; }
 __host__ __device__ constexpr int cm_k(int cm) { return (cm & 8) ? 4 : 2; }
 __host__ __device__ constexpr int cm_planes(int cm) { return cm & 3; }
@@ -325,17 +329,27 @@ inline bool linesq_layout(const HostDeviceTable& f, const HostDeviceTable* b, in
     classes.push_back(k);
     return static_cast<int>(classes.size() - 1);
   };
-  int key[256];
-  const bool hi = char_width == 2;
-  if (!hi) {
+  // slot domain: byte values; for UTF-16 the high byte when every 256-char page is uniform, else the code unit itself
+  // (16-bit lanes: thresholds below 0x8000, everything above - U+FFFF included, whose class is always 0 - one class)
+  std::vector<int> key;
+  bool hi = false, wide = false;
+  if (char_width == 1) {
+    key.resize(256);
     for (int v = 0; v < 256; v++) key[v] = id_of(key_of(v));
   } else {
-    for (int h = 0; h < 256; h++) {
-      for (int lo = 1; lo < 256; lo++)
-        if (!(key_of(h << 8 | lo) == key_of(h << 8))) return false;  // (includes U+FFFF, whose class is always 0)
-      key[h] = id_of(key_of(h << 8));
+    hi = true;
+    for (int h = 0; h < 256 && hi; h++)
+      for (int lo = 1; lo < 256 && hi; lo++) hi = key_of(h << 8 | lo) == key_of(h << 8);
+    if (hi) {
+      key.resize(256);
+      for (int h = 0; h < 256; h++) key[h] = id_of(key_of(h << 8));
+    } else {
+      wide = true;
+      key.resize(65536);
+      for (int c = 0; c < 65536; c++) key[c] = id_of(key_of(c));
     }
   }
+  auto char_of_slot = [&](int slot) { return hi ? slot << 8 : slot; };
   SwarPlan plan;
   if (!swar_solve(key, 6, plan)) return false;
   const int n = plan.n_codes;
@@ -347,9 +361,11 @@ inline bool linesq_layout(const HostDeviceTable& f, const HostDeviceTable* b, in
   // same speed on the 258-row DFA of BASELINE config 4 (1.3 instead of 1.8 wavefronts per char, but 3 % more
   // instructions in an issue-bound loop), so 16-bit entries are only used to fit automata of twice the size.
   static const Cand kCands[] = {{4, 32, 4}, {2, 32, 4}, {4, 16, 4}, {4, 8, 4}, {2, 16, 4}, {2, 8, 4}, {2, 8, 2}};
+  const int n_cands = (hi || wide) ? 6 : 7;  // 16-bit entries: byte haystacks only (kernel instantiations)
   int K = 0, R = 0, W = 0, EB = 4, lines_per_col = 0;
   uint32_t n_cols = 0;
-  for (const Cand& c : kCands) {
+  for (int ci = 0; ci < n_cands; ci++) {
+    const Cand& c = kCands[ci];
     long cols = 1;
     for (int i = 0; i < c.k; i++) cols *= n;
     int vmax = 0;
@@ -373,7 +389,7 @@ inline bool linesq_layout(const HostDeviceTable& f, const HostDeviceTable* b, in
     std::vector<int> cls(n);  // table class of every code (unused codes behave like code 0)
     for (int c = 0; c < n; c++) {
       const int slot = plan.slot_of_code[c] >= 0 ? plan.slot_of_code[c] : plan.slot_of_code[0] >= 0 ? plan.slot_of_code[0] : 128;
-      cls[c] = t.cmap[hi ? slot << 8 : slot];
+      cls[c] = t.cmap[char_of_slot(slot)];
     }
     (void)backward;
     for (int s = 0; s < rows_t; s++)
@@ -414,15 +430,25 @@ inline bool linesq_layout(const HostDeviceTable& f, const HostDeviceTable* b, in
   meta.replicated = R;
   meta.n_cols = n;
   meta.row_bytes = 0;
-  meta.char_mode = cm_swar(K, plan.planes, hi, EB == 2);
+  meta.char_mode = wide ? cm_swar_wide(K, plan.planes) : cm_swar(K, plan.planes, hi, EB == 2);
   SwarDev& q = meta.q;
   for (int p = 0; p < 3; p++) {
     const bool on = p < plan.planes;
-    q.lo[p] = on ? static_cast<uint32_t>(plan.lo[p]) * 0x01010101u : 0;
-    q.hi[p] = on ? static_cast<uint32_t>(plan.hi[p]) * 0x01010101u : 0;
+    const uint32_t rep = wide ? 0x00010001u : 0x01010101u;
+    q.lo[p] = on ? static_cast<uint32_t>(plan.lo[p]) * rep : 0;
+    q.hi[p] = on ? static_cast<uint32_t>(plan.hi[p]) * rep : 0;
     const uint32_t v = on ? static_cast<uint32_t>(plan.val[p]) : 0;
     const uint32_t un = static_cast<uint32_t>(n);
-    if (K == 4) {
+    if (wide && K == 4) {  // two chars per word (bytes 1 and 3), two words per lookup
+      q.w[p][0] = (v * un * un * un) << 8 | (v * un * un) << 24;
+      q.w[p][1] = (v * un) << 8 | v << 24;
+      q.w[p][2] = (v * un * un * un) << 24 | (v * un * un) << 8;
+      q.w[p][3] = (v * un) << 24 | v << 8;
+    } else if (wide) {
+      q.w[p][0] = (v * un) << 8 | v << 24;
+      q.w[p][2] = (v * un) << 24 | v << 8;
+      q.w[p][1] = q.w[p][3] = 0;
+    } else if (K == 4) {
       q.w[p][0] = v * un * un * un | (v * un * un) << 8 | (v * un) << 16 | v << 24;
       q.w[p][2] = v | (v * un) << 8 | (v * un * un) << 16 | (v * un * un * un) << 24;
       q.w[p][1] = q.w[p][3] = 0;
@@ -590,7 +616,7 @@ __device__ __forceinline__ void l8_word_rev(uint32_t w, const L8Ctx& cx, uint32_
 }
 template <int CM>
 struct L8Chars {
-  static constexpr int kBytes = (CM == kCmBytes || CM == kCmBytes1 || (cm_is_swar(CM) && !cm_hi(CM))) ? 1 : 2;   // bytes per char
+  static constexpr int kBytes = (CM == kCmBytes || CM == kCmBytes1 || (cm_is_swar(CM) && !cm_hi(CM) && !cm_wide(CM))) ? 1 : 2;   // bytes per char
   static constexpr int kPerChunk = 16 / kBytes;           // chars (= accept bits) per 16-byte chunk
 };
 
@@ -639,12 +665,49 @@ __device__ __forceinline__ void q_word(uint32_t w, const SwarDev& q, uint32_t& e
   }
 }
 
+// 16-bit lanes: two chars per word.  Same compares with 0x8000 in place of 0x80; a plane has bit 15 / bit 31 set,
+// i.e. byte 1 / byte 3 = 0x80, so IDP.4A works on it unchanged with the weights in bytes 1 and 3.
+// K = 4: one lookup per two words (weights [0], [1] forwards, [2], [3] backwards); K = 2: one per word.
+template <int CM, bool REV>
+__device__ __forceinline__ void q_wide(uint32_t w0, uint32_t w1, const SwarDev& q, uint32_t& e, uint32_t& mask) {
+  constexpr int P = cm_planes(CM), K = cm_k(CM);
+  constexpr uint32_t kState = L8Enc<CM>::kStateMask;
+  uint32_t d0 = 0, d1 = 0;
+  {
+    const uint32_t w80 = w0 | 0x80008000u;
+    uint32_t nm;
+    asm("lop3.b32 %0, %1, 0x80008000, 0, 0x0c;" : "=r"(nm) : "r"(w0));
+#pragma unroll
+    for (int i = 0; i < P; i++) d0 = __dp4a(((w80 - q.lo[i]) ^ (w80 - q.hi[i])) & nm, q.w[i][REV ? 2 : 0], d0);
+  }
+  {
+    const uint32_t w80 = w1 | 0x80008000u;
+    uint32_t nm;
+    asm("lop3.b32 %0, %1, 0x80008000, 0, 0x0c;" : "=r"(nm) : "r"(w1));
+    if (K == 4) d1 = d0;  // one column offset for the four chars of both words
+#pragma unroll
+    for (int i = 0; i < P; i++) d1 = __dp4a(((w80 - q.lo[i]) ^ (w80 - q.hi[i])) & nm, q.w[i][K == 4 ? (REV ? 3 : 1) : (REV ? 2 : 0)], d1);
+  }
+  if (K == 4) {
+    e = lds_tab(d1 * q.kmul + (e & kState));
+    mask = __funnelshift_l(e, mask, 4);
+  } else {
+    e = lds_tab(d0 * q.kmul + (e & kState));  // (the arguments come in walk order)
+    mask = __funnelshift_l(e, mask, 2);
+    e = lds_tab(d1 * q.kmul + (e & kState));
+    mask = __funnelshift_l(e, mask, 2);
+  }
+}
+
 // All chars of one 16-byte chunk, forwards / backwards.  Afterwards the low L8Chars<CM>::kPerChunk bits of
 // `mask` are the accept flags of these chars, bit 0 = the char walked last.
 template <int CM>
 __device__ __forceinline__ void l8_chunk(const uint4& w, const SwarDev& q, const L8Ctx& cx, uint32_t& e, uint32_t& mask) {
   if constexpr (cm_is_swar(CM)) {
-    if constexpr (cm_hi(CM)) {
+    if constexpr (cm_wide(CM)) {
+      q_wide<CM, false>(w.x, w.y, q, e, mask);
+      q_wide<CM, false>(w.z, w.w, q, e, mask);
+    } else if constexpr (cm_hi(CM)) {
       q_word<CM, false>(__byte_perm(w.x, w.y, 0x7531), q, e, mask);
       q_word<CM, false>(__byte_perm(w.z, w.w, 0x7531), q, e, mask);
     } else {
@@ -663,7 +726,10 @@ __device__ __forceinline__ void l8_chunk(const uint4& w, const SwarDev& q, const
 template <int CM>
 __device__ __forceinline__ void l8_chunk_rev(const uint4& w, const SwarDev& q, const L8Ctx& cx, uint32_t& e, uint32_t& mask) {
   if constexpr (cm_is_swar(CM)) {
-    if constexpr (cm_hi(CM)) {
+    if constexpr (cm_wide(CM)) {
+      q_wide<CM, true>(w.w, w.z, q, e, mask);
+      q_wide<CM, true>(w.y, w.x, q, e, mask);
+    } else if constexpr (cm_hi(CM)) {
       q_word<CM, true>(__byte_perm(w.z, w.w, 0x7531), q, e, mask);
       q_word<CM, true>(__byte_perm(w.x, w.y, 0x7531), q, e, mask);
     } else {

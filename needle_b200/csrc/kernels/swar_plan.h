@@ -21,27 +21,31 @@ namespace ndl {
 
 struct SwarPlan {
   int planes = 0;          // 1..3
-  int lo[3] = {0, 0, 0};   // range p is [lo, hi), 0 <= lo < hi <= 128
+  int lo[3] = {0, 0, 0};   // range p is [lo, hi), 0 <= lo < hi <= span
   int hi[3] = {0, 0, 0};
   int val[3] = {0, 0, 0};  // value added to the code inside the range
   int n_codes = 0;         // codes are 0 .. n_codes - 1 (some may be unused)
-  int code_of_slot[256];   // code of every slot value
   int slot_of_code[8];     // a representative slot value per code, -1 when the code is unused
 };
 
-// key[v]: an arbitrary class id per slot value v (byte value, or high byte of a UTF-16 char).  Succeeds when
-// all slots >= 0x80 share one key and the slots below fall into at most `max_codes` classes expressible with
-// <= 3 ranges.  Picks the plan with the fewest codes, then the fewest planes.
-inline bool swar_solve(const int (&key)[256], int max_codes, SwarPlan& out) {
-  const int z = key[128];
-  for (int v = 129; v < 256; v++)
+// key[v]: an arbitrary class id per slot value v (byte value, high byte of a UTF-16 char, or - 16-bit lanes -
+// the UTF-16 code unit itself); key.size() = 2 * span with span = 128 or 32768.  Succeeds when all slots
+// >= span (the top bit of the lane set) share one key and the slots below fall into at most `max_codes`
+// classes expressible with <= 3 ranges.  Picks the plan with the fewest codes, then the fewest planes.
+inline bool swar_solve(const std::vector<int>& key, int max_codes, SwarPlan& out) {
+  const int span = static_cast<int>(key.size() / 2);
+  const int z = key[span];
+  for (int v = span + 1; v < 2 * span; v++)
     if (key[v] != z) return false;
-  // maximal runs of equal key over [0, 128)
+  // maximal runs of equal key over [0, span)
   std::vector<int> bound{0};  // run j is [bound[j], bound[j + 1])
   std::vector<int> run_key;
-  for (int v = 1; v < 128; v++)
-    if (key[v] != key[v - 1]) bound.push_back(v);
-  bound.push_back(128);
+  for (int v = 1; v < span; v++)
+    if (key[v] != key[v - 1]) {
+      bound.push_back(v);
+      if (bound.size() > 10) return false;
+    }
+  bound.push_back(span);
   const int m = static_cast<int>(bound.size()) - 1;
   for (int j = 0; j < m; j++) run_key.push_back(key[bound[j]]);
   if (m > 9) return false;
@@ -83,14 +87,9 @@ inline bool swar_solve(const int (&key)[256], int max_codes, SwarPlan& out) {
       best.val[p] = vals[p];
     }
     for (int c = 0; c < 8; c++) best.slot_of_code[c] = -1;
-    for (int v = 0; v < 256; v++) {
-      int c = 0;
-      if (v < 128)
-        for (int p = 0; p < planes; p++)
-          if (best.lo[p] <= v && v < best.hi[p]) c += vals[p];
-      best.code_of_slot[v] = c;
-      if (best.slot_of_code[c] < 0) best.slot_of_code[c] = v;
-    }
+    for (int j = 0; j < m; j++)
+      if (best.slot_of_code[code[j]] < 0) best.slot_of_code[code[j]] = bound[j];
+    if (best.slot_of_code[0] < 0) best.slot_of_code[0] = span;  // code 0 is at least the class of the top half
   };
   // a map with a single class: one plane that never fires
   if (m == 1 && run_key[0] == z) {

@@ -376,8 +376,11 @@ def test_expected_kernels_are_selected():
     fp = fast_path(pair(workloads.REGEX["c5"])[0], 2, 2)
     assert fp == {"char_mode": 16 | 8 | 4 | 1, "replicated": 32, "has_bwd": 1, "n_cols": 2}  # class from the high byte, 1 plane
     fp = fast_path(pair(workloads.REGEX["c2"])[0], 2, 2)
-    assert fp["char_mode"] == 2  # ASCII pattern over UTF-16: one mixed page
-    assert fast_path(pair("[a-bα-ω]+")[0], 2, 2) is None  # two mixed pages: generic kernel
+    assert fp == {"char_mode": 64 | 16 | 8 | 2, "replicated": 32, "has_bwd": 0, "n_cols": 3}  # ASCII pattern over UTF-16: 16-bit lanes
+    fp = fast_path(pair(workloads.REGEX["c3"])[0], 2, 2)
+    assert fp["char_mode"] == 2  # e-mail regex over UTF-16: no compare plan, one mixed page (lines8)
+    assert fast_path(pair("[a-bα-ω]+")[0], 2, 2)["char_mode"] & 64  # two mixed pages: no lines8 mode, but two ranges on 16-bit lanes
+    assert fast_path(pair("[a-bα-ωа-я一-龥]+@")[0], 2, 2) is None  # four mixed pages, five ranges: generic kernel
     assert fast_path(pair("Holmes.{1,10}Watson|Watson.{1,10}Holmes")[0], 2, 1) is None  # 309 states x 12 classes
 
 
@@ -415,6 +418,27 @@ def test_swar_modes_all_byte_values(regex, hot, line_len):
     data[pick] = h[rng.integers(0, len(h), size=int(pick.sum()))]
     assert fast_path(pair(regex)[0], 2, 1)["char_mode"] >= 16
     assert_batch_equal(regex, 0, data, offsets)
+
+
+@pytest.mark.parametrize("line_chars", [32, 8, 128, 21, 0])
+def test_swar_utf16_16bit_lanes(line_chars):
+    """ASCII / BMP-range patterns over UTF-16 text (what a java.lang.String is): compares on 16-bit lanes."""
+    rng = np.random.default_rng(40 + line_chars)
+    n = 4000
+    lens = np.full(n, line_chars) if line_chars else rng.integers(0, 70, size=n)
+    offsets = np.zeros(n + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum(lens)
+    total = int(offsets[-1])
+    hot = np.array([ord(ch) for ch in "0123456789--- /:,.abc`dx\u0130\u0660\u03b1\u03c9\u03ca\u0410\u042f\u0430"], dtype=np.uint16)
+    chars = rng.integers(0, 0x10000, size=total).astype(np.uint16)
+    pick = rng.random(total) < 0.75
+    chars[pick] = hot[rng.integers(0, len(hot), size=int(pick.sum()))]
+    chars[::53] = 0xFFFF
+    chars[7::61] = 0x8000
+    chars[3::67] = 0x7FFF
+    for regex in (workloads.REGEX["c2"], workloads.REGEX["c4"], "[0-9]+x", "[\u03b1-\u03c9]+", "[a-c\u0410-\u042f]x", r"\d+-\d+"):
+        assert fast_path(pair(regex)[0], 2, 2)["char_mode"] & 64, regex
+        assert_batch_equal(regex, 0, chars.view(np.uint8), offsets, cw=2)
 
 
 def test_swar_utf16_all_high_bytes():

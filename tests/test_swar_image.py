@@ -22,8 +22,8 @@ def emulate(blob, mode, cw, backward, lane, data, n_chars):
     return rc, {"char_mode": info[0], "copies": info[1], "codes": info[2], "bytes": info[3]}
 
 
-def cm_swar(k, planes, hi, u16=False):
-    return 16 | (32 if u16 else 0) | (8 if k == 4 else 0) | (4 if hi else 0) | planes
+def cm_swar(k, planes, hi, u16=False, wide=False):
+    return 16 | (64 if wide else 0) | (32 if u16 else 0) | (8 if k == 4 else 0) | (4 if hi else 0) | planes
 
 
 def byte_soup(rng, n, hot):
@@ -100,7 +100,47 @@ def test_utf16_high_byte_images():
                 assert info["char_mode"] == cm_swar(4, 1, True) and info["copies"] == 32
 
 
+WIDE_CASES = [
+    # ASCII / BMP-range patterns over UTF-16 text (a java.lang.String): compares on 16-bit lanes
+    (workloads.REGEX["c2"], "0123456789--- /:,.\u0130\u0660", (4, 2, 3)),
+    (workloads.REGEX["c4"], "aaabbbc`d\u0161", (2, 2, 4)),
+    ("[0-9]+x", "0123456789x/:\u0439", None),
+    ("[\u03b1-\u03c9]+", "\u03b0\u03b1\u03c9\u03ca ab", None),
+    ("[a-c\u0410-\u042f]x", "abcdx\u040f\u0410\u042f\u0430`", None),
+]
+
+
+@pytest.mark.parametrize("regex,hot,expect", WIDE_CASES, ids=[c[0][:16] for c in WIDE_CASES])
+def test_utf16_16bit_lane_images(regex, hot, expect):
+    blob = nb.compile_to_bytes(regex, 0)
+    rng = np.random.default_rng(abs(hash(regex)) % (1 << 32))
+    hot_units = np.array([ord(ch) for ch in hot], dtype=np.uint16)
+    seen = 0
+    for n in (0, 1, 3, 4, 5, 8, 64, 3001):
+        chars = rng.integers(0, 0x10000, size=max(n, 1)).astype(np.uint16)
+        pick = rng.random(len(chars)) < 0.7
+        chars[pick] = hot_units[rng.integers(0, len(hot_units), size=int(pick.sum()))]
+        chars[::53] = 0xFFFF
+        chars[7::61] = 0x8000
+        chars[3::67] = 0x7FFF
+        data = chars.view(np.uint8)
+        for mode in (0, 1, 2):
+            for backward in (0, 1):
+                for lane in (0, 9):
+                    rc, info = emulate(blob, mode, 2, backward, lane, data, n)
+                    if backward and rc == -2:
+                        continue  # no table-driven reverse pass for this pattern / mode
+                    assert rc in (0, -1), (regex, mode, backward, n, rc, info)
+                    if rc == 0:
+                        seen += 1
+                        assert info["char_mode"] & 64, info
+                        if expect and mode == 2:
+                            k, planes, codes = expect
+                            assert info["char_mode"] == cm_swar(k, planes, False, wide=True) and info["codes"] == codes, info
+    assert seen > 0
+
+
 def test_class_maps_without_a_plan_are_refused():
-    for regex, cw in ((workloads.REGEX["c3"], 1), (workloads.REGEX["c1"], 1), ("[Ss]herlock", 1), (workloads.REGEX["c2"], 2), ("é+", 1)):
+    for regex, cw in ((workloads.REGEX["c3"], 1), (workloads.REGEX["c1"], 1), ("[Ss]herlock", 1), (workloads.REGEX["c3"], 2), ("é+", 1)):
         blob = nb.compile_to_bytes(regex, 0)
         assert emulate(blob, 2, cw, 0, 0, np.zeros(16, dtype=np.uint8), 8)[0] == -1, regex

@@ -79,6 +79,12 @@ def c5_lines(n: int, seed: int = 0x5EED0005, line_chars: int = 32):
     return chars.view(np.uint8), offsets
 
 
+def c2_lines_utf16(n: int, seed: int = 0x5EED0002, line_chars: int = 32):
+    """The C2 lines as UTF-16LE (what the JNI shim gets from a java.lang.String): n lines x 32 chars = 64 bytes."""
+    data, offsets = c2_lines(n, seed, line_chars)
+    return data.astype(np.uint16).view(np.uint8), offsets
+
+
 def c1_strings(n: int = 1000, seed: int = 0x5EED0001):
     rng = np.random.default_rng(seed)
     a = "abcdefghijklmnopqrstuvwxyz0123456789./"
