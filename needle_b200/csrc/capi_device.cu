@@ -163,8 +163,8 @@ static LinesqKernel linesq_kernel_for(int cm) {
     NDL_Q(4, 1, true) NDL_Q(4, 2, true)
     NDL_Q(2, 1, true) NDL_Q(2, 2, true)
 #undef NDL_Q
-#define NDL_Q16(pl) case cm_swar(2, pl, false, true): return linesq_kernel<cm_swar(2, pl, false, true)>;
-    NDL_Q16(1) NDL_Q16(2) NDL_Q16(3)
+#define NDL_Q16(k, pl) case cm_swar(k, pl, false, true): return linesq_kernel<cm_swar(k, pl, false, true)>;
+    NDL_Q16(2, 1) NDL_Q16(2, 2) NDL_Q16(2, 3) NDL_Q16(4, 1) NDL_Q16(4, 2) NDL_Q16(4, 3)
 #undef NDL_Q16
 #define NDL_QW(k, pl) case cm_swar_wide(k, pl): return linesq_kernel<cm_swar_wide(k, pl)>;
     NDL_QW(4, 1) NDL_QW(4, 2) NDL_QW(4, 3) NDL_QW(2, 1) NDL_QW(2, 2) NDL_QW(2, 3)
@@ -183,6 +183,7 @@ static Long8Kernel long8_kernel_for(int cm) {
     NDL_Q(4, 1, false) NDL_Q(4, 2, false) NDL_Q(4, 3, false)
     NDL_Q(2, 1, false) NDL_Q(2, 2, false) NDL_Q(2, 3, false)
     NDL_Q(2, 1, true) NDL_Q(2, 2, true) NDL_Q(2, 3, true)
+    NDL_Q(4, 1, true) NDL_Q(4, 2, true) NDL_Q(4, 3, true)
 #undef NDL_Q
     default: return nullptr;
   }
@@ -311,7 +312,7 @@ int ndl_debug_swar_emulate(const uint8_t* blob, size_t blob_len, int mode, int c
   }
   const int K = cm_k(b.char_mode), P = cm_planes(b.char_mode);
   const bool u16 = cm_u16(b.char_mode), wide = cm_wide(b.char_mode);
-  const uint32_t state_mask = u16 ? 0x3fffu : 0xffffffffu >> K;
+  const uint32_t state_mask = u16 ? 0xffffu >> K : 0xffffffffu >> K;
   const uint32_t lane_off = (static_cast<uint32_t>(lane) & b.q.copy_mask) * b.q.copy_bytes;
   const HostDeviceTable& t = backward ? bt : f;
   auto char_at = [&](uint64_t i) -> uint32_t { return char_width == 1 ? data[i] : (data[2 * i] | data[2 * i + 1] << 8); };
@@ -324,7 +325,7 @@ int ndl_debug_swar_emulate(const uint8_t* blob, size_t blob_len, int mode, int c
   };
   auto lds = [&](uint32_t addr) -> uint32_t {
     uint32_t v = 0;
-    if (addr < kQAbsTrans || addr - kQAbsTrans + 4 > img.size()) return 0xdeadbeefu;
+    if (addr < kQAbsTrans || addr - kQAbsTrans + (u16 ? 2 : 4) > img.size()) return 0xdeadbeefu;
     std::memcpy(&v, img.data() + (addr - kQAbsTrans), u16 ? 2 : 4);
     return u16 ? v << 16 | v : v;  // 16-bit entry: flags seen in the top bits, row address in the low 14
   };
@@ -367,7 +368,7 @@ int ndl_debug_swar_emulate(const uint8_t* blob, size_t blob_len, int mode, int c
     }
     uint32_t flags4 = 0;
     if (K == 4) {
-      e = lds(da * b.q.kmul + (e & state_mask));
+      e = lds((u16 ? (da * b.q.kmul) >> 7 : da * b.q.kmul) + (e & state_mask));
       flags4 = e >> 28;
     } else {
       e = lds(da * b.q.kmul + (e & state_mask));

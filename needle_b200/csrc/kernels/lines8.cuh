@@ -39,6 +39,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 #include <utility>
@@ -120,6 +122,7 @@ struct SwarDev {
   // 2,3); [2], [3] reverse pairs (bytes 3,2 and 1,0).  The first char of a group is the most significant digit.
   uint32_t w[3][4];
   uint32_t kmul;          // 128-byte lines per table column: entry address = dot product * kmul + row part
+                          // (16-bit entries at K = 4: BYTES per column, address = (dot product * kmul >> 7) + row part)
   uint32_t copy_mask;     // R - 1: lane l uses copy l & (R - 1)
   uint32_t copy_bytes;    // bytes of one copy inside a 128-byte line (4 * 32 / R)
 };
@@ -357,15 +360,24 @@ inline bool linesq_layout(const HostDeviceTable& f, const HostDeviceTable* b, in
   // candidates in order of estimated shared-memory wavefronts per char = (expected conflict degree of one
   // lookup: 1 with 32 copies, about 2 with 16, about 3 with 8, measured) / K
   struct Cand { int k, r, bytes; };
-  // 16-bit entries: (2 chars, 16 copies) takes the space of (2 chars, 8 copies of 32-bit entries) and measured the
-  // same speed on the 258-row DFA of BASELINE config 4 (1.3 instead of 1.8 wavefronts per char, but 3 % more
-  // instructions in an issue-bound loop), so 16-bit entries are only used to fit automata of twice the size.
-  static const Cand kCands[] = {{4, 32, 4}, {2, 32, 4}, {4, 16, 4}, {4, 8, 4}, {2, 16, 4}, {2, 8, 4}, {2, 8, 2}};
-  const int n_cands = (hi || wide) ? 6 : 7;  // 16-bit entries: byte haystacks only (kernel instantiations)
+  // Preference (measured on 10 M x 64-byte lines, a[ab]{k}c, exp/layout_ab.py): every 4-char table beats every 2-char
+  // table, because the 2-char walk is issue-bound (23 instructions per 4 chars against 15-16): 4.85-4.87 TB/s for
+  // (4 chars, 16-bit entries, 1 or 4 copies) - about 3.5 wavefronts per lookup, 32 lanes over 32 banks at random -
+  // against 3.90 / 3.85 / 3.72 TB/s for (2 chars, 32 / 16 / 8 copies).  16-bit entries hold a (16 - K)-bit row
+  // address + K flags, so at K = 4 a few copies - down to one - of a 1000-row automaton fit.
+  static const Cand kCands[] = {{4, 32, 4}, {4, 16, 4}, {4, 8, 4}, {4, 4, 2}, {4, 1, 2},
+                                {2, 32, 4}, {2, 16, 4}, {2, 8, 4}, {2, 8, 2}};
+  constexpr int kNCands = sizeof(kCands) / sizeof(kCands[0]);
   int K = 0, R = 0, W = 0, EB = 4, lines_per_col = 0;
   uint32_t n_cols = 0;
-  for (int ci = 0; ci < n_cands; ci++) {
+  uint32_t col_stride = 0;
+  // experiments only: NDL_Q_FORCE="k,copies,entry bytes" restricts the choice to one candidate
+  int force_k = 0, force_r = 0, force_b = 0;
+  if (const char* f = std::getenv("NDL_Q_FORCE")) std::sscanf(f, "%d,%d,%d", &force_k, &force_r, &force_b);
+  for (int ci = 0; ci < kNCands; ci++) {
     const Cand& c = kCands[ci];
+    if (force_k && (c.k != force_k || c.r != force_r || c.bytes != force_b)) continue;
+    if (c.bytes == 2 && (hi || wide)) continue;  // 16-bit entries: byte haystacks only (kernel instantiations)
     long cols = 1;
     for (int i = 0; i < c.k; i++) cols *= n;
     int vmax = 0;
@@ -373,13 +385,17 @@ inline bool linesq_layout(const HostDeviceTable& f, const HostDeviceTable* b, in
     if (vmax * (cols / n) > 255) continue;  // IDP.4A weights are bytes
     const int w = 128 / c.bytes / c.r;      // entries of one copy per 128-byte line
     const long lpc = (rows + w - 1) / w;
-    if (cols * lpc * 128 > static_cast<long>(kQMaxTransBytes)) continue;
-    if (c.bytes == 2 && kQAbsTrans + lpc * 128 > 0x4000) continue;  // a 16-bit entry holds a 14-bit row address
+    // bytes per column: whole 128-byte lines, except for a single copy, whose rows are simply contiguous
+    const long stride = c.r == 1 ? ((static_cast<long>(rows) * c.bytes + 3) & ~3L) : lpc * 128;
+    if (cols * stride > static_cast<long>(kQMaxTransBytes)) continue;
+    // a 16-bit entry holds the row address in 16 - K bits
+    if (c.bytes == 2 && kQAbsTrans + (c.r == 1 ? stride : lpc * 128) > (0x10000L >> c.k)) continue;
     K = c.k; R = c.r; W = w; EB = c.bytes; lines_per_col = static_cast<int>(lpc); n_cols = static_cast<uint32_t>(cols);
+    col_stride = static_cast<uint32_t>(stride);
     break;
   }
   if (K == 0) return false;
-  const uint32_t trans_bytes = n_cols * static_cast<uint32_t>(lines_per_col) * 128u;
+  const uint32_t trans_bytes = (n_cols * col_stride + 15u) & ~15u;
   img.assign(trans_bytes, 0);
   auto slot_off = [&](uint32_t row, uint32_t copy) {  // offset of a row's slot inside a column
     return (row / W) * 128u + copy * static_cast<uint32_t>(EB * W) + (row % W) * static_cast<uint32_t>(EB);
@@ -405,7 +421,7 @@ inline bool linesq_layout(const HostDeviceTable& f, const HostDeviceTable* b, in
         }
         for (int q = 0; q < R; q++) {
           const uint32_t target = kQAbsTrans + slot_off(static_cast<uint32_t>(row0 + st), q);
-          const uint32_t at = col * static_cast<uint32_t>(lines_per_col) * 128u + slot_off(static_cast<uint32_t>(row0 + s), q);
+          const uint32_t at = col * col_stride + slot_off(static_cast<uint32_t>(row0 + s), q);
           if (EB == 4) {
             const uint32_t v = target | flags;
             std::memcpy(img.data() + at, &v, 4);
@@ -459,7 +475,7 @@ inline bool linesq_layout(const HostDeviceTable& f, const HostDeviceTable* b, in
       q.w[p][3] = v | (v * un) << 8;
     }
   }
-  q.kmul = static_cast<uint32_t>(lines_per_col);
+  q.kmul = (EB == 2 && K == 4) ? col_stride : static_cast<uint32_t>(lines_per_col);  // bytes / 128-byte lines per column
   q.copy_mask = static_cast<uint32_t>(R - 1);
   q.copy_bytes = static_cast<uint32_t>(EB * W);
   return true;
@@ -543,9 +559,10 @@ struct L8Ctx {
 // How a table entry encodes state and accept flags, per char mode.
 template <int CM>
 struct L8Enc {
-  static constexpr uint32_t kStateMask = CM == kCmBytes1 ? 0x7fffu : cm_u16(CM) ? 0x3fffu : cm_is_swar(CM) ? (0xffffffffu >> cm_k(CM)) : kL8FlagMask;
+  static constexpr uint32_t kStateMask =
+      CM == kCmBytes1 ? 0x7fffu : cm_u16(CM) ? (0xffffu >> cm_k(CM)) : cm_is_swar(CM) ? (0xffffffffu >> cm_k(CM)) : kL8FlagMask;
   // accept flag of the LAST char of a step (kCmBytes1 entries are sign-extended, so bit 30 works there too)
-  static constexpr uint32_t kTailFlag = cm_u16(CM) ? 0x4000u : cm_is_swar(CM) ? (0x80000000u >> (cm_k(CM) - 1)) : 0x40000000u;
+  static constexpr uint32_t kTailFlag = cm_u16(CM) ? (0x8000u >> (cm_k(CM) - 1)) : cm_is_swar(CM) ? (0x80000000u >> (cm_k(CM) - 1)) : 0x40000000u;
 };
 
 // One 2-char step.  KA / KB: byte index (within the 32-bit word) that selects the class-map slot of the
@@ -642,8 +659,15 @@ __device__ __forceinline__ void q_word(uint32_t w, const SwarDev& q, uint32_t& e
     uint32_t dp = 0;
 #pragma unroll
     for (int i = 0; i < P; i++) dp = __dp4a(pl[i], q.w[i][REV ? 2 : 0], dp);
-    e = lds_tab(dp * q.kmul + (e & kState));
-    mask = __funnelshift_l(e, mask, 4);
+    if (cm_u16(CM)) {
+      // 16-bit entries, few copies (large automata): the column stride is kmul BYTES (any multiple of 2), and the
+      // dot product is 128 x column: (dp * kmul) >> 7, which folds into the add (LEA.HI).  Flags in bits 15:12.
+      e = lds_tab_u16(((dp * q.kmul) >> 7) + (e & kState));
+      mask = __funnelshift_l(e * 0x10000u, mask, 4);
+    } else {
+      e = lds_tab(dp * q.kmul + (e & kState));
+      mask = __funnelshift_l(e, mask, 4);
+    }
   } else {
     uint32_t da = 0, db = 0;
 #pragma unroll

@@ -368,7 +368,7 @@ def test_expected_kernels_are_selected():
     fp = fast_path(pair(workloads.REGEX["c3"])[0], 2, 1)
     assert fp["char_mode"] == 0 and fp["replicated"] == 32 and fp["has_bwd"] == 1  # 15 class changes: class map in shared memory
     fp = fast_path(pair(workloads.REGEX["c4"])[0], 2, 1)
-    assert fp == {"char_mode": 16 | 2, "replicated": 8, "has_bwd": 0, "n_cols": 4}  # 258 rows: 2 chars per lookup, 8 copies
+    assert fp == {"char_mode": 16 | 32 | 8 | 2, "replicated": 1, "has_bwd": 0, "n_cols": 4}  # 258 rows: 4 chars per lookup, one copy of 16-bit entries
     fp = fast_path(pair("a[ab]{7}c|b[ab]{4}d")[0], 2, 1)
     assert fp["char_mode"] == 16 | 32 | 3 and fp["replicated"] == 8  # 289 rows x 25 columns: 16-bit entries, 3 planes
     fp = fast_path(pair("a[ab]{8}c|b[ab]{6}d")[0], 2, 1)
@@ -396,6 +396,8 @@ SWAR_CASES = [
     (r"(ab|a|b-)+", b"ab-,.`c"),
     (r"a+b+", b"ab`c"),
     (r"a[ab]{7}c|b[ab]{4}d", b"aaabbbcd`e"),
+    (r"a[ab]{5}c", b"aaabbbc`d"),      # 4 chars per lookup, 4 copies of 16-bit entries
+    (r"a[ab]{3}c|b[ab]{2}d", b"aaabbbcd`e"),
 ]
 
 

@@ -38,7 +38,7 @@ def byte_soup(rng, n, hot):
 BYTE_CASES = [
     # regex, hot alphabet, expected (k, planes, copies, codes, 16-bit entries) for mode find or None = "just has to be right"
     (workloads.REGEX["c2"], b"0123456789--- /:,.", (4, 2, 32, 3, False)),
-    (workloads.REGEX["c4"], b"aaabbbc`d", (2, 2, 8, 4, False)),
+    (workloads.REGEX["c4"], b"aaabbbc`d", (4, 2, 1, 4, True)),
     (r"[0-9]+", b"0123456789/: ", None),
     (r"a*", b"a`b", None),
     (r"[^a]+b", b"ab`c\x7f\x80", None),
@@ -48,6 +48,8 @@ BYTE_CASES = [
     ("[\x7f]+a", b"a\x7f\x7e\x80\xff", None),
     (r"(ab|a|b-)+", b"ab-,.`c", None),
     (r"a[ab]{7}c|b[ab]{4}d", b"aaabbbcd`e", (2, 3, 8, 5, True)),
+    (r"a[ab]{5}c", b"aaabbbc`d", None),
+    (r"a[ab]{4}c", b"aaabbbc`d", None),
 ]
 
 
