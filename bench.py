@@ -239,6 +239,30 @@ def run_ours(args, rank, local_rank, world):
     launches = _lib.lib().ndl_kernel_launches() - launches0
     n_matches = int(matched_d.sum().item())
 
+    # ---- the same batch through ndl_match_lines (fixed-length records: no offsets array to read), reported beside `value`
+    stride_ms = stride_e2e_ms = None
+    fixed_len = bool(np.all(np.diff(off_h[:1001]) == off_h[1] - off_h[0])) and args.workload != "c3"
+    if fixed_len:
+        line_chars = int(off_h[1] - off_h[0])
+        m2, s2, e2 = torch.zeros_like(matched_d), torch.zeros_like(start_d), torch.zeros_like(end_d)
+
+        def step_stride():
+            pat.match_lines_ptrs(nb.MODE_FIND, data_d.data_ptr(), n, line_chars, cw, m2.data_ptr(), s2.data_ptr(), e2.data_ptr(),
+                                 stream=stream.cuda_stream)
+        for _ in range(args.warmup):
+            step_stride()
+        sync_all()
+        if not (torch.equal(m2, matched_d) and torch.equal(s2, start_d) and torch.equal(e2, end_d)):
+            raise SystemExit("bench: ndl_match_lines and ndl_match_batch disagree - refusing to report a number")
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(args.steps):
+            step_stride()
+        a1.record(stream)
+        sync_all()
+        stride_ms = a0.elapsed_time(a1)
+        del m2, s2, e2
+
     # ---- timed region 2: end to end from pinned host buffers through the same C-ABI call
     matched_h = torch.zeros(n_host, dtype=torch.uint8).pin_memory()
     start_h = torch.zeros(n_host, dtype=torch.int32).pin_memory()
@@ -261,14 +285,26 @@ def run_ours(args, rank, local_rank, world):
     sync_all()
     e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
     assert np.array_equal(matched_h[:ns].numpy(), em)
+    if fixed_len:
+        def step_host_stride():
+            pat.match_lines_ptrs(nb.MODE_FIND, data_p.data_ptr(), n_host, line_chars, cw, matched_h.data_ptr(), start_h.data_ptr(),
+                                 end_h.data_ptr(), mem_kind=nb.MEM_HOST, stream=stream.cuda_stream)
+        step_host_stride()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_host_stride()
+        sync_all()
+        stride_e2e_ms = (time.perf_counter() - t0) * 1e3
+        assert np.array_equal(matched_h[:ns].numpy(), em)
 
     # max over ranks, sum of bytes over ranks
-    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_ms, stride_ms or 0.0, stride_e2e_ms or 0.0], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(in_bytes), float(n_matches), float(launches), float(e2e_bytes)], dtype=torch.float64, device=dev)
     if dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms, e2e_ms = t.tolist()
+    ms, e2e_ms, stride_ms, stride_e2e_ms = t.tolist()
     job_bytes, job_matches, job_launches, job_e2e_bytes = tot.tolist()
 
     if rank == 0:
@@ -298,6 +334,14 @@ def run_ours(args, rank, local_rank, world):
                          "note": "algorithmic bytes = haystack bytes only (SURVEY.md 8d); achieved_with_metadata adds the 8 B/line of offsets the "
                                  "launch must read and the 9 B/line of results it must write (the API's own traffic, also HBM-bound)"},
         }
+        if fixed_len and stride_ms:
+            sv = job_bytes * args.steps / (stride_ms * 1e-3) / 1e9
+            line["stride_api"] = {
+                "call": "ndl_match_lines (fixed-length records, no offsets array)", "value": sv, "unit": UNIT,
+                "ms_per_step": stride_ms / args.steps, "roofline_frac": sv / world / peak,
+                "achieved_with_metadata": (in_bytes + 9 * n) / (stride_ms / args.steps * 1e-3) / 1e9,
+                "e2e": {"value": job_e2e_bytes * e2e_steps / (stride_e2e_ms * 1e-3) / 1e9, "unit": UNIT,
+                        "h2d_bytes_per_step": int(e2e_bytes), "d2h_bytes_per_step": int(9 * n_host)}}
         if world == 1:
             line["cpu_baseline"] = cpu_baseline(blob, data_h, off_h, cw)
         print(json.dumps(line), flush=True)

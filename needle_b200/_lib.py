@@ -32,7 +32,7 @@ SYMBOLS = (
     "ndl_pattern_destroy", "ndl_match_batch", "ndl_find_long", "ndl_last_error", "ndl_version",
     "ndl_device_count", "ndl_kernel_launches", "ndl_pattern_device", "ndl_find_long_from", "ndl_forwards_state_count",
     "ndl_find_long_back", "ndl_backwards_state_count", "ndl_backwards_root_accepting", "ndl_reverse_mode", "ndl_min_length",
-    "ndl_find_all_batch",
+    "ndl_find_all_batch", "ndl_match_lines",
 )
 
 _lib = None
@@ -64,6 +64,9 @@ def lib():
                                   ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                   ctypes.c_int, ctypes.c_void_p]
     L.ndl_match_batch.restype = ctypes.c_int
+    L.ndl_match_lines.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int,
+                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    L.ndl_match_lines.restype = ctypes.c_int
     L.ndl_find_all_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
     L.ndl_find_all_batch.restype = ctypes.c_int

@@ -503,15 +503,19 @@ int ndl_pattern_create(const uint8_t* blob, size_t blob_len, int device, ndl_pat
 
 void ndl_pattern_destroy(ndl_pattern* p) { free_pattern(p); }
 
-int ndl_match_batch(ndl_pattern* p, int mode, const void* data, const uint64_t* offsets, uint64_t n, int char_width,
-                    const int32_t* from, uint8_t* matched, int32_t* start, int32_t* end, int mem_kind, void* stream_) {
+}  // extern "C"
+
+// ndl_match_batch (offsets != NULL) and ndl_match_lines (offsets == NULL: haystack i = data[i * line_chars ..)).
+static int match_impl(ndl_pattern* p, int mode, const void* data, const uint64_t* offsets, uint64_t line_chars, uint64_t n, int char_width,
+                      const int32_t* from, uint8_t* matched, int32_t* start, int32_t* end, int mem_kind, void* stream_) {
   if (!p) return fail(NDL_EINVAL, "pattern must not be NULL");
   if (mode < 0 || mode > 2) return fail(NDL_EINVAL, "mode must be NDL_MODE_MATCHES, _CONTAINEDIN or _FIND");
   if (char_width != 1 && char_width != 2) return fail(NDL_EINVAL, "char_width must be 1 or 2");
   if (mem_kind != NDL_MEM_HOST && mem_kind != NDL_MEM_DEVICE) return fail(NDL_EINVAL, "mem_kind must be NDL_MEM_HOST or NDL_MEM_DEVICE");
   if (n == 0) return NDL_OK;
-  if (!offsets || !matched) return fail(NDL_EINVAL, "offsets and matched must not be NULL");
+  if (!matched) return fail(NDL_EINVAL, "matched must not be NULL");
   if (mode == NDL_MODE_FIND && (!start || !end)) return fail(NDL_EINVAL, "start and end are required for NDL_MODE_FIND");
+  if (!offsets && line_chars >= (1ull << 31)) return fail(NDL_EINVAL, "line_chars must be below 2^31");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   NDL_CUDA(cudaSetDevice(p->device));
 
@@ -519,6 +523,7 @@ int ndl_match_batch(ndl_pattern* p, int mode, const void* data, const uint64_t* 
   std::memset(&bp, 0, sizeof(bp));
   bp.n = n;
   bp.mode = mode;
+  bp.line_chars = line_chars;
   bp.min_length = p->cp.min_length;
   bp.max_length = p->cp.max_length;
   bp.reverse_mode = p->cp.reverse_mode;
@@ -538,9 +543,9 @@ int ndl_match_batch(ndl_pattern* p, int mode, const void* data, const uint64_t* 
   }
 
   // Host buffers: stage in, launch, stage out, all on `stream`, then wait.
-  if (offsets[0] > offsets[n]) return fail(NDL_EINVAL, "offsets must be non-decreasing");
-  const uint64_t base = offsets[0];
-  const uint64_t total_chars = offsets[n] - base;
+  if (offsets && offsets[0] > offsets[n]) return fail(NDL_EINVAL, "offsets must be non-decreasing");
+  const uint64_t base = offsets ? offsets[0] : 0;
+  const uint64_t total_chars = offsets ? offsets[n] - base : n * line_chars;
   const size_t data_bytes = static_cast<size_t>(total_chars) * char_width;
   std::lock_guard<std::mutex> lock(p->ws_mutex);
   Workspace& ws = p->ws;
@@ -564,21 +569,27 @@ int ndl_match_batch(ndl_pattern* p, int mode, const void* data, const uint64_t* 
   NDL_CUDA(cudaEventRecord(p->ev_start, stream));
   NDL_CUDA(cudaStreamWaitEvent(p->s_h2d, p->ev_start, 0));
   NDL_CUDA(cudaStreamWaitEvent(p->s_d2h, p->ev_start, 0));
+  auto off_at = [&](uint64_t i) { return offsets ? offsets[i] : i * line_chars; };
   uint64_t i0 = 0;
   for (int k = 0; k < n_chunks; k++) {
     uint64_t i1 = n;
     if (k + 1 < n_chunks) {
-      const uint64_t target = base + total_chars * static_cast<uint64_t>(k + 1) / static_cast<uint64_t>(n_chunks);
-      uint64_t a = i0 + 1, b = n;  // first line index >= i0 + 1 whose offset reaches the target
-      while (a < b) {
-        const uint64_t m = (a + b) / 2;
-        if (offsets[m] < target) a = m + 1; else b = m;
+      if (offsets) {
+        const uint64_t target = base + total_chars * static_cast<uint64_t>(k + 1) / static_cast<uint64_t>(n_chunks);
+        uint64_t a = i0 + 1, b = n;  // first line index >= i0 + 1 whose offset reaches the target
+        while (a < b) {
+          const uint64_t m = (a + b) / 2;
+          if (offsets[m] < target) a = m + 1; else b = m;
+        }
+        i1 = a;
+      } else {
+        i1 = n * static_cast<uint64_t>(k + 1) / static_cast<uint64_t>(n_chunks);
+        if (i1 <= i0) i1 = i0 + 1;
       }
-      i1 = a;
     }
     const uint64_t cnt = i1 - i0;
-    const size_t c0 = static_cast<size_t>(offsets[i0] - base) * char_width, c1 = static_cast<size_t>(offsets[i1] - base) * char_width;
-    NDL_CUDA(cudaMemcpyAsync(ws.offsets + i0, offsets + i0, (cnt + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, p->s_h2d));
+    const size_t c0 = static_cast<size_t>(off_at(i0) - base) * char_width, c1 = static_cast<size_t>(off_at(i1) - base) * char_width;
+    if (offsets) NDL_CUDA(cudaMemcpyAsync(ws.offsets + i0, offsets + i0, (cnt + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, p->s_h2d));
     if (c1 > c0)
       NDL_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(ws.data) + c0, static_cast<const uint8_t*>(data) + base * char_width + c0, c1 - c0,
                                cudaMemcpyHostToDevice, p->s_h2d));
@@ -587,7 +598,12 @@ int ndl_match_batch(ndl_pattern* p, int mode, const void* data, const uint64_t* 
     NDL_CUDA(cudaStreamWaitEvent(stream, p->ev_h2d[k], 0));
     BatchParams cb = bp;
     cb.n = cnt;
-    cb.offsets = ws.offsets + i0;
+    if (offsets) {
+      cb.offsets = ws.offsets + i0;
+    } else {  // line 0 of the chunk is line i0 of the batch
+      cb.offsets = nullptr;
+      cb.data = static_cast<const uint8_t*>(ws.data) + c0;
+    }
     cb.from = from ? ws.from + i0 : nullptr;
     cb.matched = ws.matched + i0;
     cb.start = ws.start + i0;
@@ -608,6 +624,18 @@ int ndl_match_batch(ndl_pattern* p, int mode, const void* data, const uint64_t* 
   return NDL_OK;
 }
 
+extern "C" {
+
+int ndl_match_batch(ndl_pattern* p, int mode, const void* data, const uint64_t* offsets, uint64_t n, int char_width,
+                    const int32_t* from, uint8_t* matched, int32_t* start, int32_t* end, int mem_kind, void* stream) {
+  if (n != 0 && !offsets) return fail(NDL_EINVAL, "offsets must not be NULL");
+  return match_impl(p, mode, data, offsets, 0, n, char_width, from, matched, start, end, mem_kind, stream);
+}
+
+int ndl_match_lines(ndl_pattern* p, int mode, const void* data, uint64_t n, uint64_t line_chars, int char_width, uint8_t* matched,
+                    int32_t* start, int32_t* end, int mem_kind, void* stream) {
+  return match_impl(p, mode, data, nullptr, line_chars, n, char_width, nullptr, matched, start, end, mem_kind, stream);
+}
 
 int ndl_find_all_batch(ndl_pattern* p, const void* data, const uint64_t* offsets, uint64_t n, int char_width, uint32_t* counts,
                        const uint64_t* match_offsets, int32_t* starts, int32_t* ends, int mem_kind, void* stream_) {

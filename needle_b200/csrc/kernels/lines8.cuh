@@ -821,7 +821,7 @@ __device__ __forceinline__ uint32_t l8_slot(uint32_t line, uint32_t c, int log2c
 // Generic per-thread walk of line i straight from global memory (irregular tiles).
 template <typename CharT>
 __device__ __forceinline__ void l8_slow_line(const BatchParams& g, uint64_t i) {
-  const uint64_t o0 = g.offsets[i], o1 = g.offsets[i + 1];
+  const uint64_t o0 = batch_off(g, i), o1 = batch_off(g, i + 1);
   const CharT* s = static_cast<const CharT*>(g.data) + o0;
   const int64_t len = static_cast<int64_t>(o1 - o0);
   if (g.mode == 0) {
@@ -859,7 +859,7 @@ __device__ __forceinline__ void l8_finish(const Lines8Params& p, const L8Ctx& cx
       else if (g.reverse_mode == 0 && p.has_bwd)  // indexBackwards (:529-586) on the staged tile
         st = l8_reverse<CM>(p, chunk_addr, ps, last, cx, g.bwd.root_accepting != 0);
       else  // single-char reverse scan (:588-614), or no resident BACKWARDS table: global tables
-        st = static_cast<int32_t>(dev_index_backwards<CharT>(g, static_cast<const CharT*>(g.data) + g.offsets[i], last - 1, 0, 0x7fffffff));
+        st = static_cast<int32_t>(dev_index_backwards<CharT>(g, static_cast<const CharT*>(g.data) + batch_off(g, i), last - 1, 0, 0x7fffffff));
     }
     g.matched[i] = last != -1;
     g.start[i] = st;
@@ -905,8 +905,8 @@ __device__ __forceinline__ void l8_run(const Lines8Params& p, const L8Ctx& cx, c
   // offsets (in chars) of line (tile * kTileLines + lane) and the next one
   auto load_offsets = [&](uint32_t tile, uint64_t& o0, uint64_t& o1) {
     const uint32_t i = tile * G::kTileLines + lane_line;
-    o0 = g.offsets[i];
-    o1 = g.offsets[i + 1];
+    o0 = batch_off(g, i);
+    o1 = batch_off(g, i + 1);
   };
   // Issue the copies of a tile whose offsets are (o0, o1); returns whether the tile is regular.
   auto stage = [&](uint64_t o0, uint64_t o1, uint32_t buf) -> bool {
@@ -1034,9 +1034,9 @@ __device__ __forceinline__ void l8_run_ragged(const Lines8Params& p, const L8Ctx
     Plan pl;
     pl.count = 0; pl.start = 0; pl.len = 0;
     if (c < hi) {
-      const uint64_t s0 = g.offsets[c] * kCharBytes;  // bytes
+      const uint64_t s0 = batch_off(g, c) * kCharBytes;  // bytes
       const uint32_t idx = min(c + lane + 1, hi);
-      const uint64_t e = g.offsets[idx] * kCharBytes;
+      const uint64_t e = batch_off(g, idx) * kCharBytes;
       const uint32_t slack = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(data) + s0) & 15u;
       const uint64_t rel_end = e - s0 + slack;  // end of this lane's line relative to the tile buffer
       const bool fits = (c + lane < hi) && rel_end <= kCap;
@@ -1204,7 +1204,7 @@ __global__ void __launch_bounds__(kL8Threads, 1) lines8_kernel(const Lines8Param
 
   // --- line geometry: byte length from the first two offsets (uniform); every tile re-checks its own lines
   const uint32_t char_bytes = (p.char_mode == kCmBytes || p.char_mode == kCmBytes1) ? 1u : 2u;
-  const uint64_t l_chars = g.offsets[1] - g.offsets[0];
+  const uint64_t l_chars = batch_off(g, 1) - batch_off(g, 0);
   const uint64_t L64 = l_chars * char_bytes;
   int log2cpl = -1;
   if (L64 >= 16 && L64 <= 256 && (L64 & (L64 - 1)) == 0) log2cpl = 31 - __clz(static_cast<uint32_t>(L64)) - 4;
@@ -1216,7 +1216,7 @@ __global__ void __launch_bounds__(kL8Threads, 1) lines8_kernel(const Lines8Param
   // length (its tiles still re-check themselves); everything else goes down the ragged path.
   if (log2cpl >= 0) {
     const uint32_t probe = static_cast<uint32_t>(min(static_cast<uint64_t>(lane) + 1, g.n - 1));
-    const bool same = g.offsets[probe + 1] - g.offsets[probe] == l_chars;
+    const bool same = batch_off(g, probe + 1) - batch_off(g, probe) == l_chars;
     if (!__all_sync(0xffffffffu, same)) log2cpl = -1;
   }
   if (!layout_ok) {
@@ -1280,13 +1280,13 @@ __global__ void __launch_bounds__(kQThreads, 1) linesq_kernel(const Lines8Params
     for (uint32_t off = 0; off < p.trans_bytes; off += 0x8000u)
       tma_bulk_g2s(kQAbsTrans + off, p.image + off, min(0x8000u, p.trans_bytes - off), kL8AbsBar);
   }
-  const uint64_t l_chars = g.offsets[1] - g.offsets[0];
+  const uint64_t l_chars = batch_off(g, 1) - batch_off(g, 0);
   const uint64_t L64 = l_chars * L8Chars<CM>::kBytes;
   int log2cpl = -1;
   if (L64 >= 16 && L64 <= 256 && (L64 & (L64 - 1)) == 0) log2cpl = 31 - __clz(static_cast<uint32_t>(L64)) - 4;
   if (log2cpl >= 0) {
     const uint32_t probe = static_cast<uint32_t>(min(static_cast<uint64_t>(lane) + 1, g.n - 1));
-    const bool same = g.offsets[probe + 1] - g.offsets[probe] == l_chars;
+    const bool same = batch_off(g, probe + 1) - batch_off(g, probe) == l_chars;
     if (!__all_sync(0xffffffffu, same)) log2cpl = -1;
   }
   if (!layout_ok) {  // unexpected shared-memory base: generic walk, one line per thread

@@ -196,6 +196,28 @@ class Pattern:
         if rc != _lib.NDL_OK:
             _raise(rc, "ndl_match_batch")
 
+    def match_lines(self, mode: int, data: np.ndarray, n: int, line_chars: int, char_width: int = 1):
+        """match_batch over n fixed-length records of `line_chars` chars from a HOST buffer (ndl_match_lines): no offsets array."""
+        data = np.ascontiguousarray(data).view(np.uint8)
+        matched = np.zeros(n, dtype=np.uint8)
+        start = np.full(n, -1, dtype=np.int32) if mode == _lib.MODE_FIND else None
+        end = np.full(n, -1, dtype=np.int32) if mode == _lib.MODE_FIND else None
+        if n:
+            rc = _lib.lib().ndl_match_lines(self._h, mode, data.ctypes.data if data.size else None, n, line_chars, char_width,
+                                            matched.ctypes.data, start.ctypes.data if start is not None else None,
+                                            end.ctypes.data if end is not None else None, _lib.MEM_HOST, None)
+            if rc != _lib.NDL_OK:
+                _raise(rc, "ndl_match_lines")
+        return matched, start, end
+
+    def match_lines_ptrs(self, mode: int, data_ptr: int, n: int, line_chars: int, char_width: int, matched_ptr: int, start_ptr: int = 0,
+                         end_ptr: int = 0, mem_kind: int = _lib.MEM_DEVICE, stream: int = 0):
+        """Raw-pointer form of match_lines (device tensors, or pinned host buffers)."""
+        rc = _lib.lib().ndl_match_lines(self._h, mode, data_ptr or None, n, line_chars, char_width, matched_ptr or None,
+                                        start_ptr or None, end_ptr or None, mem_kind, stream or None)
+        if rc != _lib.NDL_OK:
+            _raise(rc, "ndl_match_lines")
+
     def find_all_batch(self, data: np.ndarray, offsets: np.ndarray, char_width: int = 1):
         """All non-overlapping matches of every haystack (`while (m.find())`, DFACompilerTest.java:678-699) from HOST
         buffers, as CSR: returns (counts uint32[n], match_offsets uint64[n+1], starts int32[total], ends int32[total]).

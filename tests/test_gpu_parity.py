@@ -351,6 +351,39 @@ def test_find_all_batch_count_only_and_short_capacity():
     assert list(zip(starts.tolist(), ends.tolist())) == [(0, 1), (2, 4), (5, 8), (9, 13), (0, 1)]
 
 
+@pytest.mark.parametrize("line_chars", [64, 16, 256, 40, 11, 0])
+def test_match_lines_equals_match_batch_with_computed_offsets(line_chars):
+    """ndl_match_lines (fixed-length records, no offsets array) against ndl_match_batch and the oracle."""
+    rng = np.random.default_rng(line_chars)
+    n = 5000
+    alpha = np.frombuffer(b"0123456789-ab @.", dtype=np.uint8)
+    data = alpha[rng.integers(0, len(alpha), size=max(1, n * line_chars))].copy()
+    offsets = np.arange(n + 1, dtype=np.uint64) * np.uint64(line_chars)
+    for regex, cw in ((workloads.REGEX["c2"], 1), (workloads.REGEX["c3"], 1), (r"[0-9]+", 1), (workloads.REGEX["c2"], 2)):
+        if cw == 2 and line_chars % 2:
+            continue
+        pat, ora = pair(regex)
+        lc = line_chars // cw
+        offs = np.arange(n + 1, dtype=np.uint64) * np.uint64(lc)
+        for mode in (0, 1, 2):
+            got = pat.match_lines(mode, data, n, lc, cw)
+            exp = ora.match_batch(mode, data, offs, cw, threads=8)
+            for name, g, e in zip(("matched", "start", "end"), got, exp):
+                if e is not None:
+                    assert np.array_equal(g, e), (regex, cw, mode, name, line_chars)
+    # device pointers
+    torch = pytest.importorskip("torch")
+    pat, ora = pair(workloads.REGEX["c2"])
+    d = torch.from_numpy(data).cuda()
+    m = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    s_ = torch.zeros(n, dtype=torch.int32, device="cuda")
+    e_ = torch.zeros(n, dtype=torch.int32, device="cuda")
+    pat.match_lines_ptrs(2, d.data_ptr(), n, line_chars, 1, m.data_ptr(), s_.data_ptr(), e_.data_ptr())
+    torch.cuda.synchronize()
+    em, es, ee = ora.match_batch(2, data, offsets, 1, threads=8)
+    assert np.array_equal(m.cpu().numpy(), em) and np.array_equal(s_.cpu().numpy(), es) and np.array_equal(e_.cpu().numpy(), ee)
+
+
 def fast_path(pat, mode, cw):
     L = _lib.lib()
     L.ndl_debug_fast_path.argtypes = [__import__("ctypes").c_void_p, __import__("ctypes").c_int, __import__("ctypes").c_int]
