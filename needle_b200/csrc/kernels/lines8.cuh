@@ -110,7 +110,7 @@ __host__ __device__ constexpr bool cm_hi(int cm) { return (cm & 4) != 0; }
 constexpr uint32_t kQAbsTrans = 0x800;
 constexpr uint32_t kQMaxTransBytes = 0x22000;  // 139264: leaves 43 tile buffers = 21 warps
 #ifndef NDL_Q_WARPS
-#define NDL_Q_WARPS 20
+#define NDL_Q_WARPS 28
 #endif
 constexpr int kQWarps = NDL_Q_WARPS;
 constexpr int kQThreads = kQWarps * 32;
@@ -360,13 +360,16 @@ inline bool linesq_layout(const HostDeviceTable& f, const HostDeviceTable* b, in
   // candidates in order of estimated shared-memory wavefronts per char = (expected conflict degree of one
   // lookup: 1 with 32 copies, about 2 with 16, about 3 with 8, measured) / K
   struct Cand { int k, r, bytes; };
-  // Preference (measured on 10 M x 64-byte lines, a[ab]{k}c, exp/layout_ab.py): every 4-char table beats every 2-char
-  // table, because the 2-char walk is issue-bound (23 instructions per 4 chars against 15-16): 4.85-4.87 TB/s for
-  // (4 chars, 16-bit entries, 1 or 4 copies) - about 3.5 wavefronts per lookup, 32 lanes over 32 banks at random -
-  // against 3.90 / 3.85 / 3.72 TB/s for (2 chars, 32 / 16 / 8 copies).  16-bit entries hold a (16 - K)-bit row
-  // address + K flags, so at K = 4 a few copies - down to one - of a 1000-row automaton fit.
-  static const Cand kCands[] = {{4, 32, 4}, {4, 16, 4}, {4, 8, 4}, {4, 4, 2}, {4, 1, 2},
-                                {2, 32, 4}, {2, 16, 4}, {2, 8, 4}, {2, 8, 2}};
+  // Preference, measured on 10 M x 64-byte lines (exp/layout_ab.py, exp/warps_ab.sh):
+  //  * every 4-char table beats every 2-char table: the 2-char walk is issue-bound (23 instructions per 4 chars
+  //    against 15-16): a[ab]{k}c 4.85 TB/s with (4 chars, 16-bit entries, 1 copy) against 3.90 / 3.85 / 3.72 TB/s
+  //    with (2 chars, 32 / 16 / 8 copies);
+  //  * a smaller table leaves room for more warps, which matters more than conflict-free lookups: C2 with 28 warps
+  //    5.27 TB/s on 16 copies (2 wavefronts per lookup) against 5.02 on 32 copies (1 wavefront, but only 21 warps
+  //    have tile buffers), and 5.14 on a single copy of 16-bit entries (about 3.5 wavefronts);
+  //  * 16-bit entries hold a (16 - K)-bit row address + K flags, so at K = 4 one copy of a 1000-row automaton fits;
+  //    four copies of them measured worse than one on small automata (all rows of a column share one 128-byte line).
+  static const Cand kCands[] = {{4, 16, 4}, {4, 8, 4}, {4, 1, 2}, {2, 32, 4}, {2, 16, 4}, {2, 8, 4}, {2, 8, 2}};
   constexpr int kNCands = sizeof(kCands) / sizeof(kCands[0]);
   int K = 0, R = 0, W = 0, EB = 4, lines_per_col = 0;
   uint32_t n_cols = 0;
@@ -1252,7 +1255,7 @@ __global__ void __launch_bounds__(kL8Threads, 1) lines8_kernel(const Lines8Param
 // ---------------------------------------------------------------------------------------------
 // linesq_kernel: the SWAR modes.  Same tiles, same walks (l8_run / l8_run_ragged), other table image:
 // [kQAbsTrans, +trans_bytes) transition table, brought in by TMA bulk copies, then 2 KB tile buffers.
-// One instantiation per char mode; 22 warps (a full-size table leaves room for 21 pairs of tile buffers; 88 registers).
+// One instantiation per char mode; 28 warps x 72 registers (a full-size table leaves tile buffers for 21-23 of them).
 // ---------------------------------------------------------------------------------------------
 template <int CM>
 __global__ void __launch_bounds__(kQThreads, 1) linesq_kernel(const Lines8Params p) {

@@ -397,7 +397,7 @@ def test_expected_kernels_are_selected():
     """Guards against silently falling back to a slower kernel on the BASELINE configs.  char_mode >= 16 are the
     SWAR modes of linesq_kernel: 16 | 16-bit entries << 5 | (K == 4) << 3 | high-byte << 2 | planes."""
     fp = fast_path(pair(workloads.REGEX["c2"])[0], 2, 1)
-    assert fp == {"char_mode": 16 | 8 | 2, "replicated": 32, "has_bwd": 0, "n_cols": 3}  # 4 chars per lookup, 2 compare planes
+    assert fp == {"char_mode": 16 | 8 | 2, "replicated": 16, "has_bwd": 0, "n_cols": 3}  # 4 chars per lookup, 2 compare planes, 16 table copies
     fp = fast_path(pair(workloads.REGEX["c3"])[0], 2, 1)
     assert fp["char_mode"] == 0 and fp["replicated"] == 32 and fp["has_bwd"] == 1  # 15 class changes: class map in shared memory
     fp = fast_path(pair(workloads.REGEX["c4"])[0], 2, 1)
@@ -407,9 +407,9 @@ def test_expected_kernels_are_selected():
     fp = fast_path(pair("a[ab]{8}c|b[ab]{6}d")[0], 2, 1)
     assert fp is None or fp["replicated"] in (1, 32)
     fp = fast_path(pair(workloads.REGEX["c5"])[0], 2, 2)
-    assert fp == {"char_mode": 16 | 8 | 4 | 1, "replicated": 32, "has_bwd": 1, "n_cols": 2}  # class from the high byte, 1 plane
+    assert fp == {"char_mode": 16 | 8 | 4 | 1, "replicated": 16, "has_bwd": 1, "n_cols": 2}  # class from the high byte, 1 plane
     fp = fast_path(pair(workloads.REGEX["c2"])[0], 2, 2)
-    assert fp == {"char_mode": 64 | 16 | 8 | 2, "replicated": 32, "has_bwd": 0, "n_cols": 3}  # ASCII pattern over UTF-16: 16-bit lanes
+    assert fp == {"char_mode": 64 | 16 | 8 | 2, "replicated": 16, "has_bwd": 0, "n_cols": 3}  # ASCII pattern over UTF-16: 16-bit lanes
     fp = fast_path(pair(workloads.REGEX["c3"])[0], 2, 2)
     assert fp["char_mode"] == 2  # e-mail regex over UTF-16: no compare plan, one mixed page (lines8)
     assert fast_path(pair("[a-bα-ω]+")[0], 2, 2)["char_mode"] & 64  # two mixed pages: no lines8 mode, but two ranges on 16-bit lanes

@@ -37,7 +37,7 @@ def byte_soup(rng, n, hot):
 
 BYTE_CASES = [
     # regex, hot alphabet, expected (k, planes, copies, codes, 16-bit entries) for mode find or None = "just has to be right"
-    (workloads.REGEX["c2"], b"0123456789--- /:,.", (4, 2, 32, 3, False)),
+    (workloads.REGEX["c2"], b"0123456789--- /:,.", (4, 2, 16, 3, False)),
     (workloads.REGEX["c4"], b"aaabbbc`d", (4, 2, 1, 4, True)),
     (r"[0-9]+", b"0123456789/: ", None),
     (r"a*", b"a`b", None),
@@ -99,7 +99,7 @@ def test_utf16_high_byte_images():
             for backward in ((0, 1) if mode == 2 else (0,)):
                 rc, info = emulate(blob, mode, 2, backward, 3, data, n)
                 assert rc == 0, (mode, backward, n, rc, info)
-                assert info["char_mode"] == cm_swar(4, 1, True) and info["copies"] == 32
+                assert info["char_mode"] == cm_swar(4, 1, True) and info["copies"] == 16
 
 
 WIDE_CASES = [
