@@ -515,7 +515,12 @@ def cpu_baseline(blob, data, offsets, cw):
         ora.match_batch(2, data, offsets[:n + 1], cw, threads=threads)
     dt = time.perf_counter() - t0
     nbytes = int(offsets[n] - offsets[0]) * cw
-    return {"value": nbytes * reps / dt / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
+    # one thread, on a tenth of the sample: what a single Matcher loop of the reference does
+    n1 = max(1, n // 10)
+    t0 = time.perf_counter()
+    ora.match_batch(2, data, offsets[:n1 + 1], cw, threads=1)
+    single = int(offsets[n1] - offsets[0]) * cw / (time.perf_counter() - t0) / 1e9
+    return {"value": nbytes * reps / dt / 1e9, "unit": UNIT, "cores": threads, "kind": "port", "single_thread_value": single,
             "sample": f"first {n} lines ({nbytes / 1e6:.0f} MB) x {reps} passes, {threads} threads; C restatement of the generated loops, not the JVM"}
 
 

@@ -50,6 +50,13 @@ public final class GpuPattern implements Pattern, AutoCloseable {
         return r;
     }
 
+    /** {@code mode} over n fixed-length records of {@code lineChars} chars (no offsets array). */
+    public BatchResult matchLines(int mode, ByteBuffer data, int n, int lineChars, int charWidth) {
+        BatchResult r = new BatchResult(n);
+        NeedleNative.matchLines(handle, mode, data, n, lineChars, charWidth, r.matched, r.start, r.end);
+        return r;
+    }
+
     /** All non-overlapping matches of every haystack (CSR): {@code while (m.find())} per haystack, in two passes. */
     public static final class AllMatches {
         public int[] counts;

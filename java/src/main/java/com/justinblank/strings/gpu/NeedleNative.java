@@ -26,6 +26,10 @@ final class NeedleNative {
     /** One string through ndl_match_batch (GetStringCritical -> UTF-16 code units, char_width 2). Returns {matched, start, end}. */
     static native int[] matchOne(long handle, int mode, String s, int from);
 
+    /** ndl_match_lines with NDL_MEM_HOST: n fixed-length records of lineChars chars in a direct buffer, no offsets. */
+    static native void matchLines(long handle, int mode, ByteBuffer data, int n, int lineChars, int charWidth,
+                                  byte[] matched, int[] start, int[] end);
+
     /**
      * ndl_find_all_batch with NDL_MEM_HOST on direct buffers: the loop {@code while (m.find())} for every haystack.
      * Pass 1: {@code matchOffsets == null} fills {@code counts}; pass 2: {@code matchOffsets} = exclusive prefix sum

@@ -71,6 +71,22 @@ JNIEXPORT void JNICALL Java_com_justinblank_strings_gpu_NeedleNative_matchBatch(
   if (rc != NDL_OK) throw_for(env, rc);
 }
 
+JNIEXPORT void JNICALL Java_com_justinblank_strings_gpu_NeedleNative_matchLines(JNIEnv* env, jclass k, jlong h, jint mode, jobject data, jint n,
+                                                                                jint lineChars, jint charWidth, jbyteArray matched,
+                                                                                jintArray start, jintArray end) {
+  (void)k;
+  const void* d = (*env)->GetDirectBufferAddress(env, data);
+  jbyte* m = (*env)->GetPrimitiveArrayCritical(env, matched, NULL);
+  jint* s = (*env)->GetPrimitiveArrayCritical(env, start, NULL);
+  jint* e = (*env)->GetPrimitiveArrayCritical(env, end, NULL);
+  int rc = ndl_match_lines((ndl_pattern*)(intptr_t)h, mode, d, (uint64_t)n, (uint64_t)lineChars, charWidth, (uint8_t*)m, (int32_t*)s,
+                           (int32_t*)e, NDL_MEM_HOST, NULL);
+  (*env)->ReleasePrimitiveArrayCritical(env, end, e, 0);
+  (*env)->ReleasePrimitiveArrayCritical(env, start, s, 0);
+  (*env)->ReleasePrimitiveArrayCritical(env, matched, m, 0);
+  if (rc != NDL_OK) throw_for(env, rc);
+}
+
 JNIEXPORT void JNICALL Java_com_justinblank_strings_gpu_NeedleNative_findAllBatch(JNIEnv* env, jclass k, jlong h, jobject data, jobject offsets,
                                                                                   jint n, jint charWidth, jintArray counts,
                                                                                   jobject matchOffsets, jintArray starts, jintArray ends) {
