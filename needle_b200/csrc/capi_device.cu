@@ -215,7 +215,7 @@ static int launch_batch(ndl_pattern* p, const BatchParams& bp, int char_width, u
   if (bp.n == 0) return NDL_OK;
   (void)total_chars;
   const Lines8Blob& qimg = char_width == 1 ? p->q8[bp.mode] : p->q16[bp.mode];
-  if (bp.from == nullptr && qimg.ok && bp.n >= 2 && bp.n < (1ull << 31)) {
+  if (qimg.ok && bp.n >= 2 && bp.n < (1ull << 31)) {
     Lines8Params lp;
     fill_lines8_params(lp, bp, qimg);
     const uint64_t per_cta = 32ull * 21;  // lines a CTA's warps take per round
@@ -227,7 +227,7 @@ static int launch_batch(ndl_pattern* p, const BatchParams& bp, int char_width, u
     return NDL_OK;
   }
   const Lines8Blob& img = char_width == 1 ? p->l8[bp.mode] : p->l16[bp.mode];
-  if (bp.from == nullptr && img.ok && bp.n >= 2 && bp.n < (1ull << 31)) {
+  if (img.ok && bp.n >= 2 && bp.n < (1ull << 31)) {
     Lines8Params lp;
     fill_lines8_params(lp, bp, img);
     uint64_t max_tiles = (bp.n + 1023) / 1024;  // a CTA's 32 warps take 32 lines each per round

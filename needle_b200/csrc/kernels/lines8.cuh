@@ -832,9 +832,10 @@ __device__ __forceinline__ void l8_slow_line(const BatchParams& g, uint64_t i) {
   } else if (g.mode == 1) {
     g.matched[i] = dev_contained_in<CharT>(g, s, len);
   } else {
-    const int64_t e = dev_index_forwards<CharT>(g, s, len, 0);
+    const int64_t from = g.from ? g.from[i] : 0;  // find(from, to): DFAClassBuilder.java:625-659
+    const int64_t e = dev_index_forwards<CharT>(g, s, len, from);
     int64_t st = -1;
-    if (e != -1) st = (g.reverse_mode == 2) ? e - g.min_length : dev_index_backwards<CharT>(g, s, e - 1, 0, 0x7fffffff);
+    if (e != -1) st = (g.reverse_mode == 2) ? e - g.min_length : dev_index_backwards<CharT>(g, s, e - 1, from, 0x7fffffff);
     g.matched[i] = e != -1;
     g.start[i] = static_cast<int32_t>(st);
     g.end[i] = static_cast<int32_t>(e);
@@ -845,7 +846,9 @@ __device__ __forceinline__ void l8_slow_line(const BatchParams& g, uint64_t i) {
 // the end of the line is accepting (matches()); ps / chunk_addr: where the line sits in shared memory.
 template <int CM, typename CharT, typename ChunkAddr>
 __device__ __forceinline__ void l8_finish(const Lines8Params& p, const L8Ctx& cx, uint64_t i, uint32_t len_chars, int32_t last,
-                                          bool tail_accept, uint32_t ps, ChunkAddr chunk_addr) {
+                                          bool tail_accept, uint32_t ps, ChunkAddr chunk_addr, int32_t from = 0) {
+  // `from`: find(from, to) started `from` chars into the line (mode 2 only); ps, len_chars and last are relative to it,
+  // and the reverse pass stops there (its lower bound, DFAClassBuilder.java:640-659)
   const BatchParams& g = p.g;
   if (g.mode == 0) {
     bool m = tail_accept;
@@ -857,12 +860,16 @@ __device__ __forceinline__ void l8_finish(const Lines8Params& p, const L8Ctx& cx
   } else {
     int32_t st = -1;
     if (last != -1) {
-      if (g.reverse_mode == 2)  // start = end - minLength (DFAClassBuilder.java:640-646)
-        st = last - g.min_length;
-      else if (g.reverse_mode == 0 && p.has_bwd)  // indexBackwards (:529-586) on the staged tile
+      if (g.reverse_mode == 2) {  // start = end - minLength (DFAClassBuilder.java:640-646)
+        st = last + from - g.min_length;
+      } else if (g.reverse_mode == 0 && p.has_bwd) {  // indexBackwards (:529-586) on the staged tile
         st = l8_reverse<CM>(p, chunk_addr, ps, last, cx, g.bwd.root_accepting != 0);
-      else  // single-char reverse scan (:588-614), or no resident BACKWARDS table: global tables
-        st = static_cast<int32_t>(dev_index_backwards<CharT>(g, static_cast<const CharT*>(g.data) + batch_off(g, i), last - 1, 0, 0x7fffffff));
+        if (st != 0x7fffffff) st += from;
+      } else {  // single-char reverse scan (:588-614), or no resident BACKWARDS table: global tables
+        st = static_cast<int32_t>(dev_index_backwards<CharT>(g, static_cast<const CharT*>(g.data) + batch_off(g, i), last + from - 1, from,
+                                                             0x7fffffff));
+      }
+      last += from;
     }
     g.matched[i] = last != -1;
     g.start[i] = st;
@@ -1031,11 +1038,13 @@ __device__ __forceinline__ void l8_run_ragged(const Lines8Params& p, const L8Ctx
     uint32_t count;   // lines in the tile (0: none left, or the first line alone does not fit)
     uint32_t start;   // this lane's line: first byte, relative to the tile buffer
     uint32_t len;     // this lane's line length in chars
+    int32_t from;     // find(from, to): chars to skip at the start of the line; -1: out of range, walk the line from global memory
   };
+  const bool use_from = g.from != nullptr && g.mode == 2;
   // Plan the tile that starts at line c and issue its copies into buf.
   auto plan_and_stage = [&](uint32_t c, uint32_t buf) -> Plan {
     Plan pl;
-    pl.count = 0; pl.start = 0; pl.len = 0;
+    pl.count = 0; pl.start = 0; pl.len = 0; pl.from = 0;
     if (c < hi) {
       const uint64_t s0 = batch_off(g, c) * kCharBytes;  // bytes
       const uint32_t idx = min(c + lane + 1, hi);
@@ -1050,6 +1059,17 @@ __device__ __forceinline__ void l8_run_ragged(const Lines8Params& p, const L8Ctx
       if (lane == 0) prev = slack;
       pl.start = prev;
       pl.len = (end32 - prev) / kCharBytes;
+      if (use_from && lane < pl.count) {
+        // the walk starts `from` chars in; from outside [0, len) keeps the reference's corner cases (generic walk)
+        const int32_t f = g.from[c + lane];
+        if (f < 0 || (f != 0 && static_cast<uint32_t>(f) >= pl.len)) {
+          pl.from = -1;
+        } else {
+          pl.from = f;
+          pl.start += static_cast<uint32_t>(f) * kCharBytes;
+          pl.len -= static_cast<uint32_t>(f);
+        }
+      }
       if (pl.count) {
         const uint32_t total = __shfl_sync(0xffffffffu, end32, pl.count - 1);
         const uint32_t n_chunks = (total + 15) >> 4;
@@ -1073,12 +1093,21 @@ __device__ __forceinline__ void l8_run_ragged(const Lines8Params& p, const L8Ctx
     cp_async_commit();
     // pair the lines: lane k gets rank k of tile A and rank 31 - k of tile B (keys: walk iterations, has-line, lane)
     const bool own_a = lane < pa.count, own_b = lane < pb.count;
-    const uint32_t key_a = warp_sort32((own_a ? (pa.len + kPer - 1) / kPer : 0u) << 6 | (own_a ? 32u : 0u) | lane, lane);
-    const uint32_t key_b = __shfl_sync(0xffffffffu,
-                                       warp_sort32((own_b ? (pb.len + kPer - 1) / kPer : 0u) << 6 | (own_b ? 32u : 0u) | lane, lane), 31 - lane);
+    const uint32_t walk_a = (own_a && pa.from >= 0) ? (pa.len + kPer - 1) / kPer : 0u, walk_b = (own_b && pb.from >= 0) ? (pb.len + kPer - 1) / kPer : 0u;
+    const uint32_t key_a = warp_sort32(walk_a << 6 | (own_a ? 32u : 0u) | lane, lane);
+    const uint32_t key_b = __shfl_sync(0xffffffffu, warp_sort32(walk_b << 6 | (own_b ? 32u : 0u) | lane, lane), 31 - lane);
     const bool has_a = (key_a & 32u) != 0, has_b = (key_b & 32u) != 0;
-    const uint32_t start_a = __shfl_sync(0xffffffffu, pa.start, key_a & 31u), len_a = __shfl_sync(0xffffffffu, pa.len, key_a & 31u);
-    const uint32_t start_b = __shfl_sync(0xffffffffu, pb.start, key_b & 31u), len_b = __shfl_sync(0xffffffffu, pb.len, key_b & 31u);
+    const uint32_t start_a = __shfl_sync(0xffffffffu, pa.start, key_a & 31u);
+    const uint32_t start_b = __shfl_sync(0xffffffffu, pb.start, key_b & 31u);
+    int32_t from_a = 0, from_b = 0;
+    if (use_from) {
+      from_a = __shfl_sync(0xffffffffu, pa.from, key_a & 31u);
+      from_b = __shfl_sync(0xffffffffu, pb.from, key_b & 31u);
+    }
+    // (a line whose `from` is out of range is not walked here: length 0 in the loop, generic walk afterwards)
+    uint32_t len_a = __shfl_sync(0xffffffffu, pa.len, key_a & 31u), len_b = __shfl_sync(0xffffffffu, pb.len, key_b & 31u);
+    len_a = from_a < 0 ? 0u : len_a;
+    len_b = from_b < 0 ? 0u : len_b;
     cp_async_wait<0>();
     __syncwarp();
 
@@ -1136,10 +1165,14 @@ __device__ __forceinline__ void l8_run_ragged(const Lines8Params& p, const L8Ctx
         }
       }
     }
-    if (has_a)
-      l8_finish<CM, CharT>(p, cx, c + (key_a & 31u), len_a, last_a, tail_a != 0, start_a, [&](uint32_t ch) { return buf0 + l8_rslot(ch); });
-    if (has_b)
-      l8_finish<CM, CharT>(p, cx, cb + (key_b & 31u), len_b, last_b, tail_b != 0, start_b, [&](uint32_t ch) { return buf1 + l8_rslot(ch); });
+    if (has_a) {
+      if (from_a < 0) l8_slow_line<CharT>(g, c + (key_a & 31u));
+      else l8_finish<CM, CharT>(p, cx, c + (key_a & 31u), len_a, last_a, tail_a != 0, start_a, [&](uint32_t ch) { return buf0 + l8_rslot(ch); }, from_a);
+    }
+    if (has_b) {
+      if (from_b < 0) l8_slow_line<CharT>(g, cb + (key_b & 31u));
+      else l8_finish<CM, CharT>(p, cx, cb + (key_b & 31u), len_b, last_b, tail_b != 0, start_b, [&](uint32_t ch) { return buf1 + l8_rslot(ch); }, from_b);
+    }
     __syncwarp();  // every lane is done with both buffers before the next pair of tiles overwrites them
     c = cb + pb.count;
   }
@@ -1217,6 +1250,7 @@ __global__ void __launch_bounds__(kL8Threads, 1) lines8_kernel(const Lines8Param
   const uint32_t n_warps = gridDim.x * su.usable_warps;
   // The fixed-length path is taken when the batch starts with 33 equally spaced offsets of a supported
   // length (its tiles still re-check themselves); everything else goes down the ragged path.
+  if (g.from != nullptr && g.mode == 2) log2cpl = -1;  // find(from, to): the ragged walk takes the per-line start offsets
   if (log2cpl >= 0) {
     const uint32_t probe = static_cast<uint32_t>(min(static_cast<uint64_t>(lane) + 1, g.n - 1));
     const bool same = batch_off(g, probe + 1) - batch_off(g, probe) == l_chars;
@@ -1287,6 +1321,7 @@ __global__ void __launch_bounds__(kQThreads, 1) linesq_kernel(const Lines8Params
   const uint64_t L64 = l_chars * L8Chars<CM>::kBytes;
   int log2cpl = -1;
   if (L64 >= 16 && L64 <= 256 && (L64 & (L64 - 1)) == 0) log2cpl = 31 - __clz(static_cast<uint32_t>(L64)) - 4;
+  if (g.from != nullptr && g.mode == 2) log2cpl = -1;  // find(from, to): the ragged walk takes the per-line start offsets
   if (log2cpl >= 0) {
     const uint32_t probe = static_cast<uint32_t>(min(static_cast<uint64_t>(lane) + 1, g.n - 1));
     const bool same = batch_off(g, probe + 1) - batch_off(g, probe) == l_chars;

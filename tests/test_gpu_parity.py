@@ -173,6 +173,15 @@ def test_find_with_from_offsets():
     from_ = (rng.random(len(lens)) * (lens + 1)).astype(np.int32)
     for regex in (workloads.REGEX["c3"], "a*", "[a-z]+", r"\d{2}"):
         assert_batch_equal(regex, 0, data, offsets, from_=from_, modes=(2,))
+    # from beyond the end, every kernel family (packed compares, class map in shared memory, single-char reverse scan), fixed lines
+    from2 = np.minimum(from_ + rng.integers(0, 3, size=len(lens)).astype(np.int32) * (rng.random(len(lens)) < 0.1), (lens + 2).astype(np.int32))
+    for regex in (workloads.REGEX["c2"], workloads.REGEX["c3"], "[0-9]+x", "Sherlock|Street", "a*", "b|a*"):
+        assert_batch_equal(regex, 0, data, offsets, from_=from2.astype(np.int32), modes=(2,))
+    d2, o2 = workloads.c2_lines(4000)
+    f2 = rng.integers(0, 70, size=4000).astype(np.int32)
+    assert_batch_equal(workloads.REGEX["c2"], 0, d2, o2, from_=f2, modes=(2,))
+    d16, o16 = workloads.c2_lines_utf16(3000)
+    assert_batch_equal(workloads.REGEX["c2"], 0, d16, o16, cw=2, from_=rng.integers(0, 34, size=3000).astype(np.int32), modes=(2,))
 
 
 def test_empty_and_degenerate_batches():
