@@ -746,7 +746,7 @@ static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, in
     d_data = static_cast<const uint8_t*>(p->ws.data);
   }
   // scratch: SeqResult + 2 atomics + back result (kept with the pattern; calls are serialised by ws_mutex)
-  struct Scratch { SeqResult r; unsigned long long first_seg, first_bad; int64_t back; };
+  struct Scratch { SeqResult r; unsigned long long first_seg, first_bad; int64_t back; Long8Epilogue epi; };
   if (!p->ws.long_scratch) NDL_CUDA(cudaMalloc(&p->ws.long_scratch, sizeof(Scratch)));
   Scratch* d_sc = static_cast<Scratch*>(p->ws.long_scratch);
   Scratch h;
@@ -799,13 +799,6 @@ static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, in
       const uint32_t st = static_cast<uint32_t>(state);
       if (swar) return kQAbsTrans + (st / w_rows) * 128u + (st % w_rows) * eb;
       return s1 ? st : st * row_bytes;
-    };
-    auto dec = [&](uint32_t canon) -> int32_t {
-      if (swar) {
-        const uint32_t off = canon - kQAbsTrans;
-        return static_cast<int32_t>((off / 128u) * w_rows + (off % 128u) / eb);
-      }
-      return static_cast<int32_t>(s1 ? canon : canon / row_bytes);
     };
     // head: exact walk up to the first 16-byte boundary
     const uintptr_t a0 = reinterpret_cast<uintptr_t>(d_data) + static_cast<uintptr_t>(from);
@@ -867,34 +860,27 @@ static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, in
         long8_seam_kernel<<<p->sm_count * 4, 256, 0, stream>>>(ws.seam_guess, ws.seam_exit, n_tiles, &d_sc->first_bad);
         g_launches.fetch_add(1);
         NDL_CUDA(cudaGetLastError());
-        NDL_CUDA(cudaMemcpyAsync(&h, d_sc, sizeof(Scratch), cudaMemcpyDeviceToHost, stream));
+        Long8Decode dk;
+        dk.kind = swar ? 2 : s1 ? 1 : 0;
+        dk.row_bytes = row_bytes ? row_bytes : 1;
+        dk.w_rows = w_rows;
+        dk.entry_bytes = eb;
+        long8_epilogue_kernel<<<1, 32, 0, stream>>>(fwd, d_data, head_end, n, n_segs, r.state, dk, ws.seam_exit, &d_sc->first_seg,
+                                                    &d_sc->first_bad, &d_sc->epi);
+        g_launches.fetch_add(1);
+        NDL_CUDA(cudaGetLastError());
+        NDL_CUDA(cudaMemcpyAsync(&h.epi, &d_sc->epi, sizeof(Long8Epilogue), cudaMemcpyDeviceToHost, stream));
         NDL_CUDA(cudaStreamSynchronize(stream));
-        const unsigned long long kNone = ~0ull;
-        if (h.first_bad != kNone && (h.first_seg == kNone || h.first_bad <= h.first_seg)) {
+        if (h.epi.status == 1) {
           // a guess was wrong before any match: the pattern remembers further back than the warm-up.
           // Fall back to the exact sequential walk from the end of the head.
           if ((rc = seq(head_end, n, r.state, head_end, -1, r)) != NDL_OK) return rc;
           last = r.last;
-          done = true;
-        } else if (h.first_seg != kNone) {
-          // exact re-walk from the start of the first accepting segment
-          pos = head_end + static_cast<int64_t>(h.first_seg) * kLongSeg;
-          if (h.first_seg != 0) {
-            SeqResult w;
-            if ((rc = seq(pos - 16, pos, 0, pos, -1, w)) != NDL_OK) return rc;  // the verified guess
-            state = w.state;
-          }
-          if ((rc = seq(pos, n, state, pos, -1, r)) != NDL_OK) return rc;
-          last = r.last;
-          done = true;
         } else {
-          // no match in the segments: continue exactly from the (verified) exit of the last one
-          uint32_t exit_canon = 0;
-          NDL_CUDA(cudaMemcpyAsync(&exit_canon, ws.seam_exit + (n_tiles - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-          NDL_CUDA(cudaStreamSynchronize(stream));
-          state = dec(exit_canon);
-          pos = head_end + static_cast<int64_t>(n_segs) * kLongSeg;
+          r = h.epi.r;
+          last = r.last;
         }
+        done = true;
       }
       if (!done) {
         if (pos < n) {

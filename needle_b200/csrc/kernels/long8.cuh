@@ -34,9 +34,8 @@ struct SeqResult {
 // One thread walks [p0, p1) from `state0` with the generic tables; stops at DEAD.  `count_from`: accepting
 // steps at indices < count_from are ignored (warm-up).  last_init seeds `last`.
 template <typename CharT>
-__global__ void seq_walk_kernel(DevTable t, const CharT* s, int64_t p0, int64_t p1, int32_t state0, int64_t count_from,
-                                int64_t last_init, SeqResult* out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ __forceinline__ SeqResult dev_seq_walk(const DevTable& t, const CharT* s, int64_t p0, int64_t p1, int32_t state0, int64_t count_from,
+                                                  int64_t last_init) {
   const int dead = t.n_states;
   int state = state0;
   int64_t last = last_init;
@@ -46,9 +45,19 @@ __global__ void seq_walk_kernel(DevTable t, const CharT* s, int64_t p0, int64_t 
     if (state == dead) break;
     if (i >= count_from && __ldg(t.accept + state)) last = i + 1;
   }
-  out->pos = i;
-  out->last = last;
-  out->state = state;
+  SeqResult r;
+  r.pos = i;
+  r.last = last;
+  r.state = state;
+  r.pad = 0;
+  return r;
+}
+
+template <typename CharT>
+__global__ void seq_walk_kernel(DevTable t, const CharT* s, int64_t p0, int64_t p1, int32_t state0, int64_t count_from,
+                                int64_t last_init, SeqResult* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  *out = dev_seq_walk<CharT>(t, s, p0, p1, state0, count_from, last_init);
 }
 
 // Backwards: indexBackwards(index, lower) (DFAClassBuilder.java:529-614), one thread.
@@ -244,6 +253,60 @@ __global__ void __launch_bounds__(cm_is_swar(CM) ? kQThreads : kL8Threads, 1) lo
     if (lane == segs_here - 1) p.seam_exit[t] = exit_state;
   }
   cp_async_wait<0>();
+}
+
+// What ndl_find_long does once the segments are walked and the seams checked, in one launch (one host round
+// trip instead of three): decide from first_seg / first_bad, re-walk exactly from the first accepting segment (its
+// entry state re-derived from the 16 bytes before it - the verified guess), or continue from the last segment's
+// exit into the tail.  status 1: a guess was wrong before any match - the host falls back to the sequential walk.
+struct Long8Epilogue {
+  SeqResult r;
+  int32_t status;
+  int32_t pad;
+};
+struct Long8Decode {  // canonical table entry -> state id (see long8_kernel)
+  int32_t kind;       // 0 pair table (row_bytes), 1 stride-1 table (row index), 2 SWAR image
+  uint32_t row_bytes, w_rows, entry_bytes;
+};
+__global__ void long8_epilogue_kernel(DevTable t, const uint8_t* s, int64_t head_end, int64_t n, uint64_t n_segs, int32_t head_state,
+                                      Long8Decode dec, const uint32_t* seam_exit, const unsigned long long* first_seg,
+                                      const unsigned long long* first_bad, Long8Epilogue* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const unsigned long long kNone = ~0ull;
+  const unsigned long long fs = *first_seg, fb = *first_bad;
+  Long8Epilogue o;
+  o.status = 0;
+  o.pad = 0;
+  o.r.pos = head_end;
+  o.r.last = -1;
+  o.r.state = head_state;
+  o.r.pad = 0;
+  if (fb != kNone && (fs == kNone || fb <= fs)) {
+    o.status = 1;
+  } else if (fs != kNone) {
+    const int64_t pos = head_end + static_cast<int64_t>(fs) * kLongSeg;
+    int32_t state = head_state;
+    if (fs != 0) state = dev_seq_walk<uint8_t>(t, s, pos - 16, pos, 0, pos, -1).state;
+    o.r = dev_seq_walk<uint8_t>(t, s, pos, n, state, pos, -1);
+  } else {
+    const uint64_t n_tiles = (n_segs + 31) / 32;
+    const uint32_t canon = seam_exit[n_tiles - 1];
+    int32_t state;
+    if (dec.kind == 2) {
+      const uint32_t off = canon - kQAbsTrans;
+      state = static_cast<int32_t>((off / 128u) * dec.w_rows + (off % 128u) / dec.entry_bytes);
+    } else {
+      state = static_cast<int32_t>(dec.kind == 1 ? canon : canon / dec.row_bytes);
+    }
+    const int64_t pos = head_end + static_cast<int64_t>(n_segs) * kLongSeg;
+    if (pos < n) {
+      o.r = dev_seq_walk<uint8_t>(t, s, pos, n, state, pos, -1);
+    } else {
+      o.r.pos = pos;
+      o.r.state = state;
+    }
+  }
+  *out = o;
 }
 
 // Seams between tiles: lane 0 of tile t must have guessed the exit of lane 31 of tile t-1.

@@ -258,14 +258,15 @@ class Pattern:
         if mem_kind == _lib.MEM_DEVICE:
             # results are written through device pointers by the C ABI in that mode; use a small host round trip instead
             import torch
-            out = torch.zeros(3, dtype=torch.int64, device=f"cuda:{self.device}")
-            mm = torch.zeros(1, dtype=torch.uint8, device=f"cuda:{self.device}")
-            rc = _lib.lib().ndl_find_long(self._h, data_ptr or None, n_chars, char_width, from_, mm.data_ptr(), out.data_ptr(),
+            out = getattr(self, "_long_out", None)
+            if out is None:  # one small result buffer per pattern: start, end, matched (low byte of the third word)
+                out = self._long_out = torch.zeros(3, dtype=torch.int64, device=f"cuda:{self.device}")
+            rc = _lib.lib().ndl_find_long(self._h, data_ptr or None, n_chars, char_width, from_, out.data_ptr() + 16, out.data_ptr(),
                                           out.data_ptr() + 8, mem_kind, stream or None)
             if rc != _lib.NDL_OK:
                 _raise(rc, "ndl_find_long")
             o = out.cpu().tolist()
-            return bool(mm.item()), int(o[0]), int(o[1])
+            return bool(o[2] & 0xFF), int(o[0]), int(o[1])
         rc = _lib.lib().ndl_find_long(self._h, data_ptr or None, n_chars, char_width, from_, ctypes.byref(m), ctypes.byref(st),
                                       ctypes.byref(en), mem_kind, stream or None)
         if rc != _lib.NDL_OK:
