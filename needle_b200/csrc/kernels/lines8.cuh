@@ -813,6 +813,37 @@ __device__ __forceinline__ int32_t l8_reverse(const Lines8Params& p, ChunkAddr c
   return st;
 }
 
+// The single-char reverse scan (DFAClassBuilder.java:588-614) over the staged tile: the largest index below
+// `last` (relative to the byte position ps) whose char equals `rc`, or INT_MAX.  Packed equality test per word:
+// x = w ^ rc..rc has a zero lane exactly where the char matches; ((x & 0x7f..) + 0x7f..) | x has the lane's top bit
+// clear exactly for zero lanes (no carries between lanes).
+template <int CM, typename ChunkAddr>
+__device__ __forceinline__ int32_t l8_reverse_char(ChunkAddr chunk_addr, uint32_t ps, int32_t last, int rc) {
+  constexpr int kPer = L8Chars<CM>::kPerChunk, kBytes = L8Chars<CM>::kBytes;
+  constexpr uint32_t kLow = kBytes == 1 ? 0x7f7f7f7fu : 0x7fff7fffu;
+  if (kBytes == 1 && rc > 0xff) return 0x7fffffff;
+  const uint32_t rep = static_cast<uint32_t>(rc) * (kBytes == 1 ? 0x01010101u : 0x00010001u);
+  for (int32_t rem = last; rem > 0; rem -= kPer) {
+    const uint32_t h = ps + static_cast<uint32_t>(rem) * kBytes;  // window = bytes [h - 16, h)
+    const uint32_t q = h >> 4;
+    const uint4 y = lds_data16(chunk_addr(q));
+    const uint4 x = lds_data16(chunk_addr(q > 0 ? q - 1 : 0));
+    const uint4 w = L8Align(h & 15u).apply(x, y);
+    const uint32_t words[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int j = 3; j >= 0; j--) {
+      const uint32_t d = words[j] ^ rep;
+      const uint32_t z = ~((((d & kLow) + kLow) | d) | kLow);  // top bit of every lane whose char equals rc
+      if (z) {
+        const int32_t lane_in_word = (31 - __clz(z)) / (8 * kBytes);
+        const int32_t cand = rem - kPer + j * (4 / kBytes) + lane_in_word;
+        return cand >= 0 ? cand : 0x7fffffff;  // (a hit before the start of the line: every other hit lies further back)
+      }
+    }
+  }
+  return 0x7fffffff;
+}
+
 // swizzled slot (in 16-byte units) of chunk `c` of tile-local line `line`; 2^log2cpl chunks per line.
 // For lines of >= 128 bytes (cpl >= 8) the low 3 chunk bits are XORed with the line number.
 __device__ __forceinline__ uint32_t l8_slot(uint32_t line, uint32_t c, int log2cpl) {
@@ -865,7 +896,10 @@ __device__ __forceinline__ void l8_finish(const Lines8Params& p, const L8Ctx& cx
       } else if (g.reverse_mode == 0 && p.has_bwd) {  // indexBackwards (:529-586) on the staged tile
         st = l8_reverse<CM>(p, chunk_addr, ps, last, cx, g.bwd.root_accepting != 0);
         if (st != 0x7fffffff) st += from;
-      } else {  // single-char reverse scan (:588-614), or no resident BACKWARDS table: global tables
+      } else if (g.reverse_mode == 1) {  // single-char reverse scan (:588-614) on the staged tile
+        st = l8_reverse_char<CM>(chunk_addr, ps, last, g.reverse_char);
+        if (st != 0x7fffffff) st += from;
+      } else {  // no resident BACKWARDS table: global tables
         st = static_cast<int32_t>(dev_index_backwards<CharT>(g, static_cast<const CharT*>(g.data) + batch_off(g, i), last + from - 1, from,
                                                              0x7fffffff));
       }

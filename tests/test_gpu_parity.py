@@ -211,6 +211,14 @@ def test_reverse_scan_variants():
     off64 = np.arange(n + 1, dtype=np.uint64) * np.uint64(64)
     for regex in ("Sherlock|Street", "anywhere|somewhere", "([Ss]herlock)|([Hh]olmes)", "S.*e", "[a-z]+"):
         assert_batch_equal(regex, 0, fixed, off64)
+    # UTF-16 (16-bit packed compare in the single-char scan) and find(from, to): the scan stops at `from`
+    d16, o16, cw16 = nb.pack_haystacks(strings, char_width=2)
+    lens = (o16[1:] - o16[:-1]).astype(np.int64)
+    frm = (rng.random(len(lens)) * (lens + 1)).astype(np.int32)
+    for regex in ("Sherlock|Street", "anywhere|somewhere", "d|[a-c]x"):
+        assert_batch_equal(regex, 0, d16, o16, cw16)
+        assert_batch_equal(regex, 0, d16, o16, cw16, from_=frm, modes=(2,))
+        assert_batch_equal(regex, 0, data, offsets, cw, from_=frm, modes=(2,))
 
 
 def test_flags_on_gpu():
