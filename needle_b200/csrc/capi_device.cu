@@ -455,13 +455,18 @@ int ndl_pattern_create(const uint8_t* blob, size_t blob_len, int device, ndl_pat
       std::vector<uint8_t> img;
       Lines8Blob& b = cw == 1 ? p->l8[mode] : p->l16[mode];
       // preference: bank-replicated pair tables (with the BACKWARDS table resident when find() needs it),
-      // then - byte haystacks - the bank-replicated stride-1 layout, then unreplicated pair tables
+      // then - byte haystacks - the bank-replicated stride-1 layout, then unreplicated pair tables, then one plain
+      // copy of the stride-1 table
       const HostDeviceTable* bwd_t = want_bwd ? &p->tables[kBackwards].host : nullptr;
       bool ok = want_bwd && lines8_layout(fwd_t, bwd_t, cw, false, img, b);
       if (!ok) ok = lines8_layout(fwd_t, nullptr, cw, false, img, b);
-      if (!ok && cw == 1) ok = lines8_layout_s1(fwd_t, img, b);
+      if (!ok && cw == 1) ok = want_bwd && lines8_layout_s1(fwd_t, bwd_t, 32, img, b);
+      if (!ok && cw == 1) ok = lines8_layout_s1(fwd_t, nullptr, 32, img, b);
       if (!ok) ok = want_bwd && lines8_layout(fwd_t, bwd_t, cw, true, img, b);
       if (!ok) ok = lines8_layout(fwd_t, nullptr, cw, true, img, b);
+      // large tables: one plain copy of the stride-1 table (thousands of states still fit in shared memory)
+      if (!ok && cw == 1) ok = want_bwd && lines8_layout_s1(fwd_t, bwd_t, 1, img, b);
+      if (!ok && cw == 1) ok = lines8_layout_s1(fwd_t, nullptr, 1, img, b);
       if (!ok) continue;
       if (cudaMalloc(&b.dev, img.size()) != cudaSuccess ||
           cudaMemcpy(b.dev, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {

@@ -256,42 +256,64 @@ inline bool lines8_layout(const HostDeviceTable& f, const HostDeviceTable* b, in
   return true;
 }
 
-// The S1 image (byte haystacks, forward automaton only): [cmap 32 KB][trans u16].
-inline bool lines8_layout_s1(const HostDeviceTable& f, std::vector<uint8_t>& img, Lines8Blob& meta) {
-  std::vector<int> class_of_col, col_of_class(f.n_classes, -1);
+// The S1 image (byte haystacks): [cmap 32 KB][trans u16], stride-1 steps.  `copies` = 32: every entry replicated
+// per lane (64 bytes per entry, lane l reads halfword l).  `copies` = 1: a plain [row][column] array of 16-bit
+// entries - about 3.5 wavefronts per lookup (32 lanes over 32 banks at random), but it holds automata of thousands
+// of states (the large-table path of SURVEY.md 8f-3) and is still 2-3 times the generic kernel, whose tables live
+// in global memory.  With `b`, the BACKWARDS rows follow the forward rows and share the class map (joint columns),
+// so the reverse pass of find() runs on the staged tile as well.  The kernel code is the same for both: the class
+// map yields the address of (row 0, column) for the lane, the entry the row index | accept << 15.
+inline bool lines8_layout_s1(const HostDeviceTable& f, const HostDeviceTable* b, int copies, std::vector<uint8_t>& img, Lines8Blob& meta) {
+  using Key = std::pair<int, int>;
+  std::vector<Key> col_classes;
   int col_of_byte[256];
   for (int v = 0; v < 256; v++) {
-    const int k = f.cmap[v];
-    if (col_of_class[k] < 0) {
-      col_of_class[k] = static_cast<int>(class_of_col.size());
-      class_of_col.push_back(k);
+    const Key k{f.cmap[v], b ? b->cmap[v] : 0};
+    int c = -1;
+    for (size_t i = 0; i < col_classes.size(); i++)
+      if (col_classes[i] == k) c = static_cast<int>(i);
+    if (c < 0) {
+      col_classes.push_back(k);
+      c = static_cast<int>(col_classes.size() - 1);
     }
-    col_of_byte[v] = col_of_class[k];
+    col_of_byte[v] = c;
   }
-  const int C = static_cast<int>(class_of_col.size());
-  const int rows = f.n_states + 1;
+  const int C = static_cast<int>(col_classes.size());
+  const int rows_f = f.n_states + 1, rows_b = b ? b->n_states + 1 : 0, rows = rows_f + rows_b;
   if (rows > 0x7fff) return false;
-  const uint32_t row_bytes = static_cast<uint32_t>(C) * 64u;
-  const uint32_t trans_bytes = (static_cast<uint32_t>(rows) * row_bytes + 15) & ~15u;
-  if (trans_bytes > kS1MaxTransBytes) return false;
+  const uint32_t entry_bytes = copies == 32 ? 64u : 2u;  // bytes per (row, column)
+  const uint32_t row_bytes = static_cast<uint32_t>(C) * entry_bytes;
+  const uint64_t want = static_cast<uint64_t>(rows) * row_bytes;
+  if (want > kS1MaxTransBytes) return false;
+  const uint32_t trans_bytes = (static_cast<uint32_t>(want) + 15) & ~15u;
   img.assign(kS1CmapBytes + trans_bytes, 0);
   for (int v = 0; v < 256; v++)
     for (uint32_t lane = 0; lane < 32; lane++) {
-      const uint32_t cm = kS1AbsTrans + static_cast<uint32_t>(col_of_byte[v]) * 64u + lane * 2u;
+      const uint32_t cm = kS1AbsTrans + static_cast<uint32_t>(col_of_byte[v]) * entry_bytes + (copies == 32 ? lane * 2u : 0u);
       std::memcpy(img.data() + v * 128 + lane * 4, &cm, 4);
     }
-  for (int s = 0; s < rows; s++)
-    for (int c = 0; c < C; c++) {
-      const int t = f.trans[static_cast<size_t>(s) * f.n_classes + class_of_col[c]];
-      const uint16_t e = static_cast<uint16_t>(t | (f.accept[t] ? 0x8000 : 0));
-      for (uint32_t lane = 0; lane < 32; lane++)
-        std::memcpy(img.data() + kS1CmapBytes + static_cast<uint32_t>(s) * row_bytes + static_cast<uint32_t>(c) * 64u + lane * 2u, &e, 2);
-    }
+  auto emit = [&](const HostDeviceTable& t, int row0, bool backward) {
+    for (int s = 0; s <= t.n_states; s++)
+      for (int c = 0; c < C; c++) {
+        const int k = backward ? col_classes[c].second : col_classes[c].first;
+        const int nx = t.trans[static_cast<size_t>(s) * t.n_classes + k];
+        const uint16_t e = static_cast<uint16_t>((row0 + nx) | (t.accept[nx] ? 0x8000 : 0));
+        const uint32_t at = kS1CmapBytes + static_cast<uint32_t>(row0 + s) * row_bytes + static_cast<uint32_t>(c) * entry_bytes;
+        for (uint32_t lane = 0; lane < (copies == 32 ? 32u : 1u); lane++) std::memcpy(img.data() + at + lane * 2u, &e, 2);
+      }
+  };
+  emit(f, 0, false);
   meta = Lines8Blob();
+  if (b) {
+    emit(*b, rows_f, true);
+    meta.has_bwd = true;
+    meta.bwd_root = static_cast<uint32_t>(rows_f);
+    meta.bwd_dead = static_cast<uint32_t>(rows_f + b->n_states);
+  }
   meta.trans_bytes = trans_bytes;
   meta.root_entry = 0;
   meta.fwd_dead = static_cast<uint32_t>(f.n_states);
-  meta.replicated = 32;
+  meta.replicated = copies;
   meta.n_cols = C;
   meta.row_bytes = row_bytes;
   meta.char_mode = kCmBytes1;
@@ -620,7 +642,7 @@ __device__ __forceinline__ void l8_word(uint32_t w, const L8Ctx& cx, uint32_t& e
 }
 template <int CM>
 __device__ __forceinline__ void l8_word_rev(uint32_t w, const L8Ctx& cx, uint32_t& e, uint32_t& mask) {
-  if (CM == kCmBytes1) {  // (no BACKWARDS table is resident in the S1 layout; kept for completeness)
+  if (CM == kCmBytes1) {
     l8_step1<3>(w, cx, e, mask);
     l8_step1<2>(w, cx, e, mask);
     l8_step1<1>(w, cx, e, mask);

@@ -230,11 +230,27 @@ def test_flags_on_gpu():
         assert_batch_equal(regex, fl, data, offsets, cw)
 
 
-def test_large_table_pattern_uses_generic_path():
-    # 309-state search DFA (HolmesNearWatson snapshot): too big for the replicated shared-memory image
+def test_large_table_patterns():
+    # 309-state search DFA (HolmesNearWatson snapshot) and its 2467-state sibling: too big for the replicated shared-memory
+    # images, one plain copy of the stride-1 table fits (with the BACKWARDS rows for the first); a[ab]{11}c: 4097 states, 16-bit
+    # 4-char table too large, plain stride-1 table fits, as does the one of a[ab]{12}c (8193 states x 4 columns)
     data, offsets = workloads.c2_lines(2000)
-    text = np.frombuffer(("Holmes and then Watson " * 6000).encode()[:2000 * 64], dtype=np.uint8)
-    assert_batch_equal("Holmes.{1,10}Watson|Watson.{1,10}Holmes", 0, text, offsets)
+    text = np.frombuffer(("Holmes and then Watson said to Mr. Sherlock Holmes, my dear Watson " * 2000).encode()[:2000 * 64], dtype=np.uint8)
+    rng = np.random.default_rng(3)
+    ragged = np.zeros(2001, dtype=np.uint64)
+    ragged[1:] = np.cumsum(rng.integers(0, 129, size=2000))
+    ragged = np.minimum(ragged, len(text)).astype(np.uint64)
+    for regex in ("Holmes.{1,10}Watson|Watson.{1,10}Holmes", "Holmes.{0,25}Watson|Watson.{0,25}Holmes"):
+        fp = fast_path(pair(regex)[0], 2, 1)
+        assert fp is not None and fp["char_mode"] == 3 and fp["replicated"] == 1, fp
+        assert_batch_equal(regex, 0, text, offsets)
+        assert_batch_equal(regex, 0, text, ragged)
+    assert fast_path(pair("Holmes.{1,10}Watson|Watson.{1,10}Holmes")[0], 2, 1)["has_bwd"] == 1
+    ab = (rng.integers(0, 2, size=2000 * 64, dtype=np.uint8) + ord("a")).astype(np.uint8)
+    ab[rng.integers(0, len(ab), size=3000)] = ord("c")
+    for regex in ("a[ab]{11}c", "a[ab]{12}c"):
+        assert_batch_equal(regex, 0, ab, offsets)
+    assert fast_path(pair("a[ab]{11}c")[0], 2, 1)["replicated"] == 1 and fast_path(pair("a[ab]{12}c")[0], 2, 1)["replicated"] == 1
 
 
 def test_device_memory_entry_point():
@@ -431,7 +447,8 @@ def test_expected_kernels_are_selected():
     assert fp["char_mode"] == 2  # e-mail regex over UTF-16: no compare plan, one mixed page (lines8)
     assert fast_path(pair("[a-bα-ω]+")[0], 2, 2)["char_mode"] & 64  # two mixed pages: no lines8 mode, but two ranges on 16-bit lanes
     assert fast_path(pair("[a-bα-ωа-я一-龥]+@")[0], 2, 2) is None  # four mixed pages, five ranges: generic kernel
-    assert fast_path(pair("Holmes.{1,10}Watson|Watson.{1,10}Holmes")[0], 2, 1) is None  # 309 states x 12 classes
+    fp = fast_path(pair("Holmes.{1,10}Watson|Watson.{1,10}Holmes")[0], 2, 1)
+    assert fp["char_mode"] == 3 and fp["replicated"] == 1 and fp["has_bwd"] == 1  # 309 states x 12 classes: one plain stride-1 table
 
 
 SWAR_CASES = [
