@@ -38,3 +38,30 @@ for name, regex in (("c3 e-mail", workloads.REGEX["c3"]), ("c2 ssn", workloads.R
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 20
         print(f"{name:10s} mode {mode}: {nbytes / ms / 1e6:8.1f} GB/s  ({ms:.3f} ms, matches {int(m.sum())})", flush=True)
+
+# long lines: fixed 512 / 4096 bytes and ragged 200..3000
+for label, lens in (("fixed 512 B", np.full(1_000_000, 512)), ("fixed 4 KB", np.full(125_000, 4096)),
+                    ("ragged 200..3000 B", np.random.default_rng(3).integers(200, 3000, size=300_000))):
+    offl = np.zeros(len(lens) + 1, dtype=np.uint64)
+    offl[1:] = np.cumsum(lens)
+    tot = int(offl[-1])
+    src, _ = workloads.c3_lines(tot // 60 + 1000)
+    dl = torch.from_numpy(np.ascontiguousarray(src[:tot])).to(dev)
+    ol = torch.from_numpy(offl.view(np.int64)).to(dev)
+    nl = len(lens)
+    for name, regex in (("c3 e-mail", workloads.REGEX["c3"]), ("c2 ssn", workloads.REGEX["c2"])):
+        pat = nb.Pattern(nb.compile_to_bytes(regex, 0), device=0)
+
+        def step():
+            pat.match_batch_ptrs(2, dl.data_ptr(), ol.data_ptr(), nl, 1, m.data_ptr(), s.data_ptr(), e.data_ptr(), stream=stream.cuda_stream)
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        print(f"{label:20s} {name:10s} find: {tot / ms / 1e6:8.1f} GB/s  ({ms:.3f} ms)", flush=True)

@@ -899,9 +899,10 @@ __device__ __forceinline__ void l8_slow_line(const BatchParams& g, uint64_t i) {
 // the end of the line is accepting (matches()); ps / chunk_addr: where the line sits in shared memory.
 template <int CM, typename CharT, typename ChunkAddr>
 __device__ __forceinline__ void l8_finish(const Lines8Params& p, const L8Ctx& cx, uint64_t i, uint32_t len_chars, int32_t last,
-                                          bool tail_accept, uint32_t ps, ChunkAddr chunk_addr, int32_t from = 0) {
+                                          bool tail_accept, uint32_t ps, ChunkAddr chunk_addr, int32_t from = 0, bool resident = true) {
   // `from`: find(from, to) started `from` chars into the line (mode 2 only); ps, len_chars and last are relative to it,
-  // and the reverse pass stops there (its lower bound, DFAClassBuilder.java:640-659)
+  // and the reverse pass stops there (its lower bound, DFAClassBuilder.java:640-659).  `resident`: the whole line is in
+  // the tile buffer that chunk_addr addresses (false for streamed lines: their reverse pass reads global memory).
   const BatchParams& g = p.g;
   if (g.mode == 0) {
     bool m = tail_accept;
@@ -915,13 +916,13 @@ __device__ __forceinline__ void l8_finish(const Lines8Params& p, const L8Ctx& cx
     if (last != -1) {
       if (g.reverse_mode == 2) {  // start = end - minLength (DFAClassBuilder.java:640-646)
         st = last + from - g.min_length;
-      } else if (g.reverse_mode == 0 && p.has_bwd) {  // indexBackwards (:529-586) on the staged tile
+      } else if (g.reverse_mode == 0 && p.has_bwd && resident) {  // indexBackwards (:529-586) on the staged tile
         st = l8_reverse<CM>(p, chunk_addr, ps, last, cx, g.bwd.root_accepting != 0);
         if (st != 0x7fffffff) st += from;
-      } else if (g.reverse_mode == 1) {  // single-char reverse scan (:588-614) on the staged tile
+      } else if (g.reverse_mode == 1 && resident) {  // single-char reverse scan (:588-614) on the staged tile
         st = l8_reverse_char<CM>(chunk_addr, ps, last, g.reverse_char);
         if (st != 0x7fffffff) st += from;
-      } else {  // no resident BACKWARDS table: global tables
+      } else {  // no resident BACKWARDS table, or the line is not resident (streamed lines): global memory
         st = static_cast<int32_t>(dev_index_backwards<CharT>(g, static_cast<const CharT*>(g.data) + batch_off(g, i), last + from - 1, from,
                                                              0x7fffffff));
       }
@@ -1077,6 +1078,100 @@ __device__ __forceinline__ uint32_t warp_sort32(uint32_t key, uint32_t lane) {
   return key;
 }
 
+// Long lines (more than about 256 bytes: fewer than 8 fit a tile, down to none).  One line per lane as before, but
+// streamed: every round stages the next 64 bytes of each lane's own line (the lane's four aligned 16-byte chunks, in the
+// swizzled slots of a 64-byte-line tile) while the previous 64 are walked, so lines of any length keep all 32 lanes
+// busy and nothing depends on a line fitting a buffer.  Chunk k of a line is needed as the upper half of walk step
+// k - 1 (the lower half is carried in registers), so a round performs the steps whose upper chunk it holds.
+// The reverse pass of find() reads global memory (the line is not resident).
+template <int CM, typename CharT>
+__device__ __forceinline__ void l8_stream_group(const Lines8Params& p, const L8Ctx& cx, const uint32_t buf0, const uint32_t buf1,
+                                                const uint32_t lane, const uint32_t c, const uint32_t m, const bool use_from) {
+  constexpr uint32_t kCharBytes = L8Chars<CM>::kBytes;
+  constexpr uint32_t kPer = L8Chars<CM>::kPerChunk;
+  const BatchParams& g = p.g;
+  const uint8_t* const data = static_cast<const uint8_t*>(g.data);
+  const bool own = lane < m;
+  uint64_t o0 = 0;
+  uint32_t len = 0;
+  int32_t from = 0;
+  bool slow = false;
+  if (own) {
+    o0 = batch_off(g, c + lane);
+    const uint64_t l64 = batch_off(g, c + lane + 1) - o0;
+    slow = l64 >= (1ull << 31);
+    len = slow ? 0u : static_cast<uint32_t>(l64);
+    if (use_from && !slow) {
+      const int32_t f = g.from[c + lane];
+      if (f < 0 || (f != 0 && static_cast<uint32_t>(f) >= len)) {
+        slow = true;  // keeps the reference's corner cases: generic walk
+        len = 0;
+      } else {
+        from = f;
+        o0 += static_cast<uint32_t>(f);
+        len -= static_cast<uint32_t>(f);
+      }
+    }
+  }
+  const uint64_t sb = o0 * kCharBytes, eb = sb + static_cast<uint64_t>(len) * kCharBytes;  // bytes walked: [sb, eb)
+  const uint32_t a = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(data) + sb) & 15u;
+  const uint64_t ab = sb - a;
+  const uint32_t iters = (len + kPer - 1) / kPer;
+  const uint32_t chunks = iters ? iters + 1 : 0;  // chunk k = bytes [ab + 16 k, + 16)
+  const uint32_t max_pieces = __reduce_max_sync(0xffffffffu, (chunks + 3) / 4);
+  auto stage = [&](uint32_t j, uint32_t buf) {
+#pragma unroll
+    for (uint32_t cc = 0; cc < 4; cc++) {
+      const uint32_t k = 4 * j + cc;
+      if (k < chunks && ab + 16ull * k < eb) cp_async16(buf + (l8_slot(lane, cc, 2) << 4), data + ab + 16ull * k);
+    }
+    cp_async_commit();
+  };
+  uint32_t cur = buf0, nxt = buf1;
+  if (max_pieces) stage(0, cur);
+  const L8Align al(a);
+  uint32_t e = cx.root, pos = 0;
+  int32_t last = g.fwd.root_accepting ? 0 : -1;
+  uint32_t tail_bit = g.fwd.root_accepting ? 1u : 0u;
+  uint4 x = make_uint4(0, 0, 0, 0);
+  for (uint32_t j = 0; j < max_pieces; j++) {
+    if (j + 1 < max_pieces) stage(j + 1, nxt);
+    else cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+#pragma unroll
+    for (uint32_t cc = 0; cc < 4; cc++) {
+      const uint32_t k = 4 * j + cc;
+      if (k < chunks) {
+        const uint4 y = lds_data16(cur + (l8_slot(lane, cc, 2) << 4));
+        if (k > 0 && pos < len) {  // walk step k - 1: chars [pos, pos + kPer)
+          const uint4 w = al.apply(x, y);
+          uint32_t mask = 0;
+          l8_chunk<CM>(w, p.q, cx, e, mask);
+          const uint32_t valid = min(kPer, len - pos);
+          mask >>= (kPer - valid);
+          const int32_t cand = static_cast<int32_t>(pos + valid + 1) - __ffs(mask);
+          last = mask ? cand : last;
+          tail_bit = mask & 1u;
+          pos += kPer;
+          if ((e & L8Enc<CM>::kStateMask) == cx.fwd_dead) pos = len;
+        }
+        x = y;
+      }
+    }
+    __syncwarp();
+    const uint32_t tmp = cur;
+    cur = nxt;
+    nxt = tmp;
+  }
+  cp_async_wait<0>();
+  if (own) {
+    if (slow) l8_slow_line<CharT>(g, c + lane);
+    else l8_finish<CM, CharT>(p, cx, c + lane, len, last, tail_bit != 0, 0u, [&](uint32_t) { return buf0; }, from, false);
+  }
+  __syncwarp();
+}
+
 template <int CM>
 __device__ __forceinline__ void l8_run_ragged(const Lines8Params& p, const L8Ctx& cx, const uint32_t buf0, const uint32_t buf1,
                                               const uint32_t lane, const uint32_t warp_global, const uint32_t n_warps) {
@@ -1095,12 +1190,13 @@ __device__ __forceinline__ void l8_run_ragged(const Lines8Params& p, const L8Ctx
     uint32_t start;   // this lane's line: first byte, relative to the tile buffer
     uint32_t len;     // this lane's line length in chars
     int32_t from;     // find(from, to): chars to skip at the start of the line; -1: out of range, walk the line from global memory
+    bool stream;      // fewer than 8 of the remaining lines fit the buffer: long lines, nothing was staged (l8_stream_group)
   };
   const bool use_from = g.from != nullptr && g.mode == 2;
   // Plan the tile that starts at line c and issue its copies into buf.
   auto plan_and_stage = [&](uint32_t c, uint32_t buf) -> Plan {
     Plan pl;
-    pl.count = 0; pl.start = 0; pl.len = 0; pl.from = 0;
+    pl.count = 0; pl.start = 0; pl.len = 0; pl.from = 0; pl.stream = false;
     if (c < hi) {
       const uint64_t s0 = batch_off(g, c) * kCharBytes;  // bytes
       const uint32_t idx = min(c + lane + 1, hi);
@@ -1110,6 +1206,11 @@ __device__ __forceinline__ void l8_run_ragged(const Lines8Params& p, const L8Ctx
       const bool fits = (c + lane < hi) && rel_end <= kCap;
       const uint32_t ballot = __ballot_sync(0xffffffffu, fits);
       pl.count = __popc(ballot);  // offsets are non-decreasing, so `fits` is a prefix
+      if (pl.count < 8 && pl.count < hi - c) {
+        pl.stream = true;
+        pl.count = 0;
+        return pl;
+      }
       const uint32_t end32 = static_cast<uint32_t>(rel_end);
       uint32_t prev = __shfl_up_sync(0xffffffffu, end32, 1);
       if (lane == 0) prev = slack;
@@ -1139,11 +1240,13 @@ __device__ __forceinline__ void l8_run_ragged(const Lines8Params& p, const L8Ctx
   uint32_t c = lo;
   while (c < hi) {
     const Plan pa = plan_and_stage(c, buf0);
-    if (pa.count == 0) {  // a line longer than the buffer: walk it straight from global memory
-      if (lane == 0) l8_slow_line<CharT>(g, c);
-      c += 1;
+    if (pa.stream) {  // long lines: stream the next 32, one per lane
+      const uint32_t m = min(32u, hi - c);
+      l8_stream_group<CM, CharT>(p, cx, buf0, buf1, lane, c, m, use_from);
+      c += m;
       continue;
     }
+    if (pa.count == 0) break;  // (c == hi)
     const uint32_t cb = c + pa.count;
     const Plan pb = plan_and_stage(cb, buf1);  // count 0: nothing left, or a long line that the next round handles
     cp_async_commit();

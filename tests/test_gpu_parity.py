@@ -417,6 +417,46 @@ def test_match_lines_equals_match_batch_with_computed_offsets(line_chars):
     assert np.array_equal(m.cpu().numpy(), em) and np.array_equal(s_.cpu().numpy(), es) and np.array_equal(e_.cpu().numpy(), ee)
 
 
+@pytest.mark.parametrize("shape", ["fixed512", "fixed1000", "fixed4096", "ragged_long", "mixed", "huge"])
+def test_long_lines_are_streamed(shape):
+    """Lines longer than a tile buffer holds eight of (down to lines of many KB): one line per lane, streamed 64 bytes at a time."""
+    rng = np.random.default_rng(len(shape))
+    if shape.startswith("fixed"):
+        L = int(shape[5:])
+        n = 700
+        lens = np.full(n, L)
+    elif shape == "ragged_long":
+        n = 900
+        lens = rng.integers(200, 3000, size=n)
+    elif shape == "mixed":
+        n = 3000
+        lens = np.where(rng.random(n) < 0.2, rng.integers(300, 6000, size=n), rng.integers(0, 100, size=n))
+    else:
+        n = 40
+        lens = rng.integers(50_000, 200_000, size=n)
+    offsets = np.zeros(n + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum(lens)
+    total = int(offsets[-1])
+    words = [b"Sherlock", b"Street", b"Holmes and Watson ", b" 123-45-6789 ", b"bob@example.org", b" ", b"x", b"0", b"-", b"\n", b"abababababc"]
+    blob = b"".join(words[j] for j in rng.integers(0, len(words), total // 6 + 16))
+    data = np.frombuffer(blob[:total], dtype=np.uint8).copy()
+    # sparse variant of the same batch, so that most lines are walked to their very end
+    sparse = data.copy()
+    sparse[rng.random(total) < 0.97] = ord("q")
+    frm = (rng.random(n) * (lens + 1)).astype(np.int32)
+    for regex in (workloads.REGEX["c2"], workloads.REGEX["c3"], workloads.REGEX["c4"], "Sherlock|Street", "[Ss]herlock",
+                  "Holmes.{1,10}Watson|Watson.{1,10}Holmes", "[0-9]+x", "q*"):
+        for d in (data, sparse):
+            assert_batch_equal(regex, 0, d, offsets)
+        assert_batch_equal(regex, 0, data, offsets, from_=frm, modes=(2,))
+    if shape in ("fixed512", "ragged_long", "mixed"):
+        wide = data[:total - total % 2].astype(np.uint16)
+        o16 = offsets.copy()
+        o16[-1] = min(int(o16[-1]), len(wide))
+        for regex in (workloads.REGEX["c2"], workloads.REGEX["c3"], "Sherlock|Street"):
+            assert_batch_equal(regex, 0, wide.view(np.uint8), o16, cw=2)
+
+
 def fast_path(pat, mode, cw):
     L = _lib.lib()
     L.ndl_debug_fast_path.argtypes = [__import__("ctypes").c_void_p, __import__("ctypes").c_int, __import__("ctypes").c_int]
