@@ -594,19 +594,32 @@ static int match_impl(ndl_pattern* p, int mode, const void* data, const uint64_t
     }
     const uint64_t cnt = i1 - i0;
     const size_t c0 = static_cast<size_t>(off_at(i0) - base) * char_width, c1 = static_cast<size_t>(off_at(i1) - base) * char_width;
-    if (offsets) NDL_CUDA(cudaMemcpyAsync(ws.offsets + i0, offsets + i0, (cnt + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, p->s_h2d));
+    // data first, so that the link is busy while the host looks at this chunk's offsets
     if (c1 > c0)
       NDL_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(ws.data) + c0, static_cast<const uint8_t*>(data) + base * char_width + c0, c1 - c0,
                                cudaMemcpyHostToDevice, p->s_h2d));
+    // Equally spaced offsets need not cross the link (8 bytes per line: 11 % of the traffic of 64-byte lines): the host
+    // checks every offset of the chunk - exact, and hidden behind the copy above - and the kernel computes them instead.
+    bool uniform = false;
+    uint64_t stride = 0;
+    if (offsets) {
+      stride = offsets[i0 + 1] - offsets[i0];
+      uint64_t bad = 0;
+      const uint64_t* o = offsets + i0;
+      for (uint64_t j = 1; j <= cnt; j++) bad |= (o[j] - o[0]) ^ (j * stride);
+      uniform = bad == 0 && stride < (1ull << 31);
+      if (!uniform) NDL_CUDA(cudaMemcpyAsync(ws.offsets + i0, offsets + i0, (cnt + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, p->s_h2d));
+    }
     if (from) NDL_CUDA(cudaMemcpyAsync(ws.from + i0, from + i0, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, p->s_h2d));
     NDL_CUDA(cudaEventRecord(p->ev_h2d[k], p->s_h2d));
     NDL_CUDA(cudaStreamWaitEvent(stream, p->ev_h2d[k], 0));
     BatchParams cb = bp;
     cb.n = cnt;
-    if (offsets) {
+    if (offsets && !uniform) {
       cb.offsets = ws.offsets + i0;
     } else {  // line 0 of the chunk is line i0 of the batch
       cb.offsets = nullptr;
+      cb.line_chars = offsets ? stride : line_chars;
       cb.data = static_cast<const uint8_t*>(ws.data) + c0;
     }
     cb.from = from ? ws.from + i0 : nullptr;
