@@ -60,6 +60,7 @@ struct Workspace {
   // ndl_find_long: per-tile seam arrays and the scratch record
   uint32_t* seam_guess = nullptr;
   uint32_t* seam_exit = nullptr;
+  uint32_t* seam_acc = nullptr;
   size_t seam_cap = 0;
   void* long_scratch = nullptr;
 };
@@ -79,6 +80,7 @@ struct ndl_pattern {
   Lines8Blob q16[3];  // per mode: same for UTF-16 haystacks
   std::mutex ws_mutex;
   Workspace ws;
+  bool long8_ready = false;  // long8_kernel's shared-memory attribute is set
   // host-buffer calls are pipelined in chunks: H2D on s_h2d, kernels on the caller's stream, D2H on s_d2h
   static constexpr int kMaxChunks = 16;
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -124,6 +126,7 @@ static void free_pattern(ndl_pattern* p) {
   cudaFree(p->ws.end);
   cudaFree(p->ws.seam_guess);
   cudaFree(p->ws.seam_exit);
+  cudaFree(p->ws.seam_acc);
   cudaFree(p->ws.long_scratch);
   cudaSetDevice(prev);
   delete p;
@@ -848,11 +851,13 @@ static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, in
         if (n_tiles > ws.seam_cap) {
           cudaFree(ws.seam_guess);
           cudaFree(ws.seam_exit);
-          ws.seam_guess = ws.seam_exit = nullptr;
+          cudaFree(ws.seam_acc);
+          ws.seam_guess = ws.seam_exit = ws.seam_acc = nullptr;
           ws.seam_cap = 0;
           const size_t cap = n_tiles + n_tiles / 8 + 16;
           NDL_CUDA(cudaMalloc(&ws.seam_guess, cap * sizeof(uint32_t)));
           NDL_CUDA(cudaMalloc(&ws.seam_exit, cap * sizeof(uint32_t)));
+          NDL_CUDA(cudaMalloc(&ws.seam_acc, cap * sizeof(uint32_t)));
           ws.seam_cap = cap;
         }
         NDL_CUDA(cudaMemsetAsync(&d_sc->first_seg, 0xff, 2 * sizeof(unsigned long long), stream));
@@ -867,10 +872,14 @@ static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, in
         lp.q = img.q;
         lp.seam_guess = ws.seam_guess;
         lp.seam_exit = ws.seam_exit;
+        lp.seam_acc = ws.seam_acc;
         lp.first_seg = &d_sc->first_seg;
         lp.first_bad = &d_sc->first_bad;
         Long8Kernel kern = long8_kernel_for(img.char_mode);
-        NDL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kL8DynSmem));
+        if (!p->long8_ready) {  // once per pattern (calls are serialised by ws_mutex)
+          NDL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kL8DynSmem));
+          p->long8_ready = true;
+        }
         const uint32_t block_warps = swar ? kQWarps : kL8Warps;
         uint64_t want = (n_tiles + block_warps - 1) / block_warps;
         int blocks = static_cast<int>(want < static_cast<uint64_t>(p->sm_count) ? want : p->sm_count);
@@ -885,7 +894,7 @@ static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, in
         dk.row_bytes = row_bytes ? row_bytes : 1;
         dk.w_rows = w_rows;
         dk.entry_bytes = eb;
-        long8_epilogue_kernel<<<1, 32, 0, stream>>>(fwd, d_data, head_end, n, n_segs, r.state, dk, ws.seam_exit, &d_sc->first_seg,
+        long8_epilogue_kernel<<<1, 32, 0, stream>>>(fwd, d_data, head_end, n, n_segs, r.state, dk, ws.seam_exit, ws.seam_acc, &d_sc->first_seg,
                                                     &d_sc->first_bad, &d_sc->epi);
         g_launches.fetch_add(1);
         NDL_CUDA(cudaGetLastError());

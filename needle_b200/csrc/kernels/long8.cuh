@@ -109,6 +109,8 @@ struct Long8Params {
   SwarDev q;               // SWAR modes
   uint32_t* seam_guess;    // [n_tiles] lane 0's guessed entry (canonical)
   uint32_t* seam_exit;     // [n_tiles] exit of the tile's last segment (canonical)
+  uint32_t* seam_acc;      // [n_tiles] of the tile's first accepting segment: (canonical state at the start of its first
+                           // accepting 64-byte piece) << 2 | piece - where the exact re-walk starts
   unsigned long long* first_seg;   // atomicMin: first segment (global index) that saw an accepting state
   unsigned long long* first_bad;   // atomicMin: first segment whose in-warp check failed
 };
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(cm_is_swar(CM) ? kQThreads : kL8Threads, 1) lo
     // warm-up bytes: the 16 bytes before the lane's segment, straight from global memory
     uint4 pre = make_uint4(0, 0, 0, 0);
     if (act && (seg0 + lane) != 0) pre = *reinterpret_cast<const uint4*>(p.data + (seg0 + lane) * kLongSeg - 16);
-    uint32_t e = cx.root, mask = 0, any = 0, guess = 0;
+    uint32_t e = cx.root, mask = 0, any = 0, guess = 0, acc_at = 0;
 #pragma unroll 1
     for (uint32_t j = 0; j < 4; j++) {
       if (j < 3) stage(t, j + 1, nxt);
@@ -226,13 +228,17 @@ __global__ void __launch_bounds__(cm_is_swar(CM) ? kQThreads : kL8Threads, 1) lo
           if (seg0 + lane == 0) e = p.entry0 + lane_off;  // the head was walked exactly
           guess = (e & kStateMask) - lane_off;
         }
+        const uint32_t e_piece = (e & kStateMask) - lane_off;
+        uint32_t any_piece = 0;
 #pragma unroll
         for (uint32_t c = 0; c < 4; c++) {  // 2. the piece itself
           const uint4 w = lds_data16(cur + (l8_slot(lane, c, LOG2CPL) << 4));
           mask = 0;
           l8_chunk<CM>(w, p.q, cx, e, mask);
-          any |= mask;
+          any_piece |= mask;
         }
+        if (any == 0 && any_piece != 0) acc_at = e_piece << 2 | j;
+        any |= any_piece;
       }
       __syncwarp();
       const uint32_t tmp = cur;
@@ -251,6 +257,7 @@ __global__ void __launch_bounds__(cm_is_swar(CM) ? kQThreads : kL8Threads, 1) lo
       if (acc_lanes) atomicMin(p.first_seg, static_cast<unsigned long long>(seg0 + (__ffs(acc_lanes) - 1)));
     }
     if (lane == segs_here - 1) p.seam_exit[t] = exit_state;
+    if (acc_lanes && lane == static_cast<uint32_t>(__ffs(acc_lanes) - 1)) p.seam_acc[t] = acc_at;
   }
   cp_async_wait<0>();
 }
@@ -269,7 +276,7 @@ struct Long8Decode {  // canonical table entry -> state id (see long8_kernel)
   uint32_t row_bytes, w_rows, entry_bytes;
 };
 __global__ void long8_epilogue_kernel(DevTable t, const uint8_t* s, int64_t head_end, int64_t n, uint64_t n_segs, int32_t head_state,
-                                      Long8Decode dec, const uint32_t* seam_exit, const unsigned long long* first_seg,
+                                      Long8Decode dec, const uint32_t* seam_exit, const uint32_t* seam_acc, const unsigned long long* first_seg,
                                       const unsigned long long* first_bad, Long8Epilogue* out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const unsigned long long kNone = ~0ull;
@@ -281,23 +288,23 @@ __global__ void long8_epilogue_kernel(DevTable t, const uint8_t* s, int64_t head
   o.r.last = -1;
   o.r.state = head_state;
   o.r.pad = 0;
+  auto decode = [&](uint32_t canon) -> int32_t {
+    if (dec.kind == 2) {
+      const uint32_t off = canon - kQAbsTrans;
+      return static_cast<int32_t>((off / 128u) * dec.w_rows + (off % 128u) / dec.entry_bytes);
+    }
+    return static_cast<int32_t>(dec.kind == 1 ? canon : canon / dec.row_bytes);
+  };
   if (fb != kNone && (fs == kNone || fb <= fs)) {
     o.status = 1;
   } else if (fs != kNone) {
-    const int64_t pos = head_end + static_cast<int64_t>(fs) * kLongSeg;
-    int32_t state = head_state;
-    if (fs != 0) state = dev_seq_walk<uint8_t>(t, s, pos - 16, pos, 0, pos, -1).state;
-    o.r = dev_seq_walk<uint8_t>(t, s, pos, n, state, pos, -1);
+    // the first accepting segment published the (verified) state at the start of its first accepting 64-byte piece
+    const uint32_t acc = seam_acc[fs / 32];
+    const int64_t pos = head_end + static_cast<int64_t>(fs) * kLongSeg + static_cast<int64_t>(acc & 3u) * 64;
+    o.r = dev_seq_walk<uint8_t>(t, s, pos, n, decode(acc >> 2), pos, -1);
   } else {
     const uint64_t n_tiles = (n_segs + 31) / 32;
-    const uint32_t canon = seam_exit[n_tiles - 1];
-    int32_t state;
-    if (dec.kind == 2) {
-      const uint32_t off = canon - kQAbsTrans;
-      state = static_cast<int32_t>((off / 128u) * dec.w_rows + (off % 128u) / dec.entry_bytes);
-    } else {
-      state = static_cast<int32_t>(dec.kind == 1 ? canon : canon / dec.row_bytes);
-    }
+    const int32_t state = decode(seam_exit[n_tiles - 1]);
     const int64_t pos = head_end + static_cast<int64_t>(n_segs) * kLongSeg;
     if (pos < n) {
       o.r = dev_seq_walk<uint8_t>(t, s, pos, n, state, pos, -1);
