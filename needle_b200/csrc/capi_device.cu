@@ -11,12 +11,14 @@
 #include <string>
 #include <vector>
 
+#define NDL_MAIN_TU  // this file compiles the non-template kernels of the shared headers
 #include "capi_internal.h"
 #include "device_image.h"
 #include "host/pattern.h"
 #include "kernels/generic.cuh"
 #include "kernels/lines8.cuh"
 #include "kernels/long8.cuh"
+#include "kernels/instances.h"
 #include "needle_b200.h"
 
 namespace ndl {
@@ -155,42 +157,6 @@ static int ensure_workspace(Workspace& ws, size_t data_bytes, uint64_t n, bool w
     ws.n_cap = cap;
   }
   return NDL_OK;
-}
-
-// The linesq_kernel instantiation of a SWAR char mode (nullptr: not instantiated).
-typedef void (*LinesqKernel)(const Lines8Params);
-static LinesqKernel linesq_kernel_for(int cm) {
-  switch (cm) {
-#define NDL_Q(k, pl, hi) case cm_swar(k, pl, hi): return linesq_kernel<cm_swar(k, pl, hi)>;
-    NDL_Q(4, 1, false) NDL_Q(4, 2, false) NDL_Q(4, 3, false)
-    NDL_Q(2, 1, false) NDL_Q(2, 2, false) NDL_Q(2, 3, false)
-    NDL_Q(4, 1, true) NDL_Q(4, 2, true)
-    NDL_Q(2, 1, true) NDL_Q(2, 2, true)
-#undef NDL_Q
-#define NDL_Q16(k, pl) case cm_swar(k, pl, false, true): return linesq_kernel<cm_swar(k, pl, false, true)>;
-    NDL_Q16(2, 1) NDL_Q16(2, 2) NDL_Q16(2, 3) NDL_Q16(4, 1) NDL_Q16(4, 2) NDL_Q16(4, 3)
-#undef NDL_Q16
-#define NDL_QW(k, pl) case cm_swar_wide(k, pl): return linesq_kernel<cm_swar_wide(k, pl)>;
-    NDL_QW(4, 1) NDL_QW(4, 2) NDL_QW(4, 3) NDL_QW(2, 1) NDL_QW(2, 2) NDL_QW(2, 3)
-#undef NDL_QW
-    default: return nullptr;
-  }
-}
-
-// The long8_kernel instantiation of a byte char mode (nullptr: not instantiated).
-typedef void (*Long8Kernel)(const Long8Params);
-static Long8Kernel long8_kernel_for(int cm) {
-  switch (cm) {
-    case kCmBytes: return long8_kernel<kCmBytes>;
-    case kCmBytes1: return long8_kernel<kCmBytes1>;
-#define NDL_Q(k, pl, u16) case cm_swar(k, pl, false, u16): return long8_kernel<cm_swar(k, pl, false, u16)>;
-    NDL_Q(4, 1, false) NDL_Q(4, 2, false) NDL_Q(4, 3, false)
-    NDL_Q(2, 1, false) NDL_Q(2, 2, false) NDL_Q(2, 3, false)
-    NDL_Q(2, 1, true) NDL_Q(2, 2, true) NDL_Q(2, 3, true)
-    NDL_Q(4, 1, true) NDL_Q(4, 2, true) NDL_Q(4, 3, true)
-#undef NDL_Q
-    default: return nullptr;
-  }
 }
 
 static void fill_lines8_params(Lines8Params& lp, const BatchParams& bp, const Lines8Blob& img) {

@@ -1375,6 +1375,7 @@ struct L8Setup {
   }
 };
 
+#ifdef NDL_MAIN_TU  // non-template kernels are compiled by capi_device.cu only (the inst_*.cu files share this header)
 __global__ void __launch_bounds__(kL8Threads, 1) lines8_kernel(const Lines8Params p) {
   const uint32_t tid = threadIdx.x;
   const uint32_t lane = tid & 31, warp = tid >> 5;
@@ -1444,6 +1445,8 @@ __global__ void __launch_bounds__(kL8Threads, 1) lines8_kernel(const Lines8Param
   else if (p.char_mode == kCmHi) l8_dispatch<kCmHi>(p, cx, log2cpl, buf0, buf1, lane, warp_global, n_warps);
   else l8_dispatch<kCmMixed>(p, cx, log2cpl, buf0, buf1, lane, warp_global, n_warps);
 }
+
+#endif  // NDL_MAIN_TU
 
 // ---------------------------------------------------------------------------------------------
 // linesq_kernel: the SWAR modes.  Same tiles, same walks (l8_run / l8_run_ragged), other table image:

@@ -275,6 +275,7 @@ struct Long8Decode {  // canonical table entry -> state id (see long8_kernel)
   int32_t kind;       // 0 pair table (row_bytes), 1 stride-1 table (row index), 2 SWAR image
   uint32_t row_bytes, w_rows, entry_bytes;
 };
+#ifdef NDL_MAIN_TU
 __global__ void long8_epilogue_kernel(DevTable t, const uint8_t* s, int64_t head_end, int64_t n, uint64_t n_segs, int32_t head_state,
                                       Long8Decode dec, const uint32_t* seam_exit, const uint32_t* seam_acc, const unsigned long long* first_seg,
                                       const unsigned long long* first_bad, Long8Epilogue* out) {
@@ -316,11 +317,16 @@ __global__ void long8_epilogue_kernel(DevTable t, const uint8_t* s, int64_t head
   *out = o;
 }
 
+#endif  // NDL_MAIN_TU
+
 // Seams between tiles: lane 0 of tile t must have guessed the exit of lane 31 of tile t-1.
+#ifdef NDL_MAIN_TU
 __global__ void long8_seam_kernel(const uint32_t* guess, const uint32_t* exit_state, uint64_t n_tiles, unsigned long long* first_bad) {
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
   for (uint64_t t = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x + 1; t < n_tiles; t += stride)
     if (guess[t] != exit_state[t - 1]) atomicMin(first_bad, t * 32ull);
 }
+
+#endif  // NDL_MAIN_TU
 
 }  // namespace ndl
