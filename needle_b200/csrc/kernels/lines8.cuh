@@ -1117,7 +1117,9 @@ __device__ __forceinline__ void l8_stream_group(const Lines8Params& p, const L8C
   const uint32_t a = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(data) + sb) & 15u;
   const uint64_t ab = sb - a;
   const uint32_t iters = (len + kPer - 1) / kPer;
-  const uint32_t chunks = iters ? iters + 1 : 0;  // chunk k = bytes [ab + 16 k, + 16)
+  // 16-byte aligned lines (fixed-length records, mostly): walk step k reads chunk k itself - no realignment, no carry
+  const bool aligned = __all_sync(0xffffffffu, a == 0 || iters == 0);
+  const uint32_t chunks = iters ? iters + (aligned ? 0u : 1u) : 0;  // chunk k = bytes [ab + 16 k, + 16)
   const uint32_t max_pieces = __reduce_max_sync(0xffffffffu, (chunks + 3) / 4);
   auto stage = [&](uint32_t j, uint32_t buf) {
 #pragma unroll
@@ -1134,29 +1136,35 @@ __device__ __forceinline__ void l8_stream_group(const Lines8Params& p, const L8C
   int32_t last = g.fwd.root_accepting ? 0 : -1;
   uint32_t tail_bit = g.fwd.root_accepting ? 1u : 0u;
   uint4 x = make_uint4(0, 0, 0, 0);
+  auto walk_step = [&](const uint4& w) {  // chars [pos, pos + kPer)
+    uint32_t mask = 0;
+    l8_chunk<CM>(w, p.q, cx, e, mask);
+    const uint32_t valid = min(kPer, len - pos);
+    mask >>= (kPer - valid);
+    const int32_t cand = static_cast<int32_t>(pos + valid + 1) - __ffs(mask);
+    last = mask ? cand : last;
+    tail_bit = mask & 1u;
+    pos += kPer;
+    if ((e & L8Enc<CM>::kStateMask) == cx.fwd_dead) pos = len;
+  };
   for (uint32_t j = 0; j < max_pieces; j++) {
     if (j + 1 < max_pieces) stage(j + 1, nxt);
     else cp_async_commit();
     cp_async_wait<1>();
     __syncwarp();
+    if (aligned) {
 #pragma unroll
-    for (uint32_t cc = 0; cc < 4; cc++) {
-      const uint32_t k = 4 * j + cc;
-      if (k < chunks) {
-        const uint4 y = lds_data16(cur + (l8_slot(lane, cc, 2) << 4));
-        if (k > 0 && pos < len) {  // walk step k - 1: chars [pos, pos + kPer)
-          const uint4 w = al.apply(x, y);
-          uint32_t mask = 0;
-          l8_chunk<CM>(w, p.q, cx, e, mask);
-          const uint32_t valid = min(kPer, len - pos);
-          mask >>= (kPer - valid);
-          const int32_t cand = static_cast<int32_t>(pos + valid + 1) - __ffs(mask);
-          last = mask ? cand : last;
-          tail_bit = mask & 1u;
-          pos += kPer;
-          if ((e & L8Enc<CM>::kStateMask) == cx.fwd_dead) pos = len;
+      for (uint32_t cc = 0; cc < 4; cc++)
+        if (4 * j + cc < chunks && pos < len) walk_step(lds_data16(cur + (l8_slot(lane, cc, 2) << 4)));
+    } else {
+#pragma unroll
+      for (uint32_t cc = 0; cc < 4; cc++) {
+        const uint32_t k = 4 * j + cc;
+        if (k < chunks) {
+          const uint4 y = lds_data16(cur + (l8_slot(lane, cc, 2) << 4));
+          if (k > 0 && pos < len) walk_step(al.apply(x, y));  // walk step k - 1
+          x = y;
         }
-        x = y;
       }
     }
     __syncwarp();
