@@ -899,10 +899,12 @@ __device__ __forceinline__ void l8_slow_line(const BatchParams& g, uint64_t i) {
 // the end of the line is accepting (matches()); ps / chunk_addr: where the line sits in shared memory.
 template <int CM, typename CharT, typename ChunkAddr>
 __device__ __forceinline__ void l8_finish(const Lines8Params& p, const L8Ctx& cx, uint64_t i, uint32_t len_chars, int32_t last,
-                                          bool tail_accept, uint32_t ps, ChunkAddr chunk_addr, int32_t from = 0, bool resident = true) {
+                                          bool tail_accept, uint32_t ps, ChunkAddr chunk_addr, int32_t from = 0, bool resident = true,
+                                          bool have_st = false, int32_t st_pre = 0) {
   // `from`: find(from, to) started `from` chars into the line (mode 2 only); ps, len_chars and last are relative to it,
   // and the reverse pass stops there (its lower bound, DFAClassBuilder.java:640-659).  `resident`: the whole line is in
   // the tile buffer that chunk_addr addresses (false for streamed lines: their reverse pass reads global memory).
+  // `have_st`: the table-driven reverse pass has been run already (pooled across the warp), st_pre is its result.
   const BatchParams& g = p.g;
   if (g.mode == 0) {
     bool m = tail_accept;
@@ -917,7 +919,7 @@ __device__ __forceinline__ void l8_finish(const Lines8Params& p, const L8Ctx& cx
       if (g.reverse_mode == 2) {  // start = end - minLength (DFAClassBuilder.java:640-646)
         st = last + from - g.min_length;
       } else if (g.reverse_mode == 0 && p.has_bwd && resident) {  // indexBackwards (:529-586) on the staged tile
-        st = l8_reverse<CM>(p, chunk_addr, ps, last, cx, g.bwd.root_accepting != 0);
+        st = have_st ? st_pre : l8_reverse<CM>(p, chunk_addr, ps, last, cx, g.bwd.root_accepting != 0);
         if (st != 0x7fffffff) st += from;
       } else if (g.reverse_mode == 1 && resident) {  // single-char reverse scan (:588-614) on the staged tile
         st = l8_reverse_char<CM>(chunk_addr, ps, last, g.reverse_char);
@@ -1332,13 +1334,43 @@ __device__ __forceinline__ void l8_run_ragged(const Lines8Params& p, const L8Ctx
         }
       }
     }
+    // Table-driven reverse passes (find() of a variable-length pattern), pooled: only the lines that matched need one,
+    // so when there are at most 32 of them in the two tiles they are dealt out one per lane - job j goes to lane j -
+    // instead of every lane looping over its own two lines while most lanes idle.
+    int32_t st_a = 0, st_b = 0;
+    bool pooled = false;
+    if (g.mode == 2 && g.reverse_mode == 0 && p.has_bwd != 0) {
+      const bool need_a = has_a && from_a >= 0 && last_a != -1, need_b = has_b && from_b >= 0 && last_b != -1;
+      const uint32_t jobs_a = __ballot_sync(0xffffffffu, need_a), jobs_b = __ballot_sync(0xffffffffu, need_b);
+      const uint32_t n_a = __popc(jobs_a), total = n_a + __popc(jobs_b);
+      pooled = total <= 32;  // (when most lines match, every lane has work anyway: each walks its own)
+      if (pooled && total) {
+        const uint32_t lt = (1u << lane) - 1u;
+        const uint32_t my_job_a = __popc(jobs_a & lt), my_job_b = n_a + __popc(jobs_b & lt);  // job numbers of this lane's own lines
+        const bool valid = lane < total, from_b_tile = lane >= n_a;
+        const uint32_t src = valid ? __fns(from_b_tile ? jobs_b : jobs_a, 0, static_cast<int>(from_b_tile ? lane - n_a : lane) + 1) : 0u;
+        const uint32_t ps_a = __shfl_sync(0xffffffffu, start_a, src), ps_b = __shfl_sync(0xffffffffu, start_b, src);
+        const int32_t l_a = __shfl_sync(0xffffffffu, last_a, src), l_b = __shfl_sync(0xffffffffu, last_b, src);
+        int32_t st = 0;
+        if (valid) {
+          const uint32_t buf = from_b_tile ? buf1 : buf0;
+          st = l8_reverse<CM>(p, [&](uint32_t ch) { return buf + l8_rslot(ch); }, from_b_tile ? ps_b : ps_a, from_b_tile ? l_b : l_a, cx,
+                              g.bwd.root_accepting != 0);
+        }
+        // hand the results back to the lanes that own the lines
+        st_a = __shfl_sync(0xffffffffu, st, my_job_a & 31u);
+        st_b = __shfl_sync(0xffffffffu, st, my_job_b & 31u);
+      }
+    }
     if (has_a) {
       if (from_a < 0) l8_slow_line<CharT>(g, c + (key_a & 31u));
-      else l8_finish<CM, CharT>(p, cx, c + (key_a & 31u), len_a, last_a, tail_a != 0, start_a, [&](uint32_t ch) { return buf0 + l8_rslot(ch); }, from_a);
+      else l8_finish<CM, CharT>(p, cx, c + (key_a & 31u), len_a, last_a, tail_a != 0, start_a, [&](uint32_t ch) { return buf0 + l8_rslot(ch); }, from_a,
+                                true, pooled, st_a);
     }
     if (has_b) {
       if (from_b < 0) l8_slow_line<CharT>(g, cb + (key_b & 31u));
-      else l8_finish<CM, CharT>(p, cx, cb + (key_b & 31u), len_b, last_b, tail_b != 0, start_b, [&](uint32_t ch) { return buf1 + l8_rslot(ch); }, from_b);
+      else l8_finish<CM, CharT>(p, cx, cb + (key_b & 31u), len_b, last_b, tail_b != 0, start_b, [&](uint32_t ch) { return buf1 + l8_rslot(ch); }, from_b,
+                                true, pooled, st_b);
     }
     __syncwarp();  // every lane is done with both buffers before the next pair of tiles overwrites them
     c = cb + pb.count;
