@@ -424,19 +424,22 @@ int ndl_pattern_create(const uint8_t* blob, size_t blob_len, int device, ndl_pat
       const bool want_bwd = mode == NDL_MODE_FIND && p->cp.reverse_mode == kReverseTable;
       std::vector<uint8_t> img;
       Lines8Blob& b = cw == 1 ? p->l8[mode] : p->l16[mode];
-      // preference: bank-replicated pair tables (with the BACKWARDS table resident when find() needs it), then
-      // unreplicated pair tables, then - byte haystacks - the bank-replicated stride-1 layout, then one plain copy of it
       const HostDeviceTable* bwd_t = want_bwd ? &p->tables[kBackwards].host : nullptr;
-      bool ok = want_bwd && lines8_layout(fwd_t, bwd_t, cw, false, img, b);
+      // Preference (measured, exp/large_table.py): bank-replicated pair tables, unreplicated pair tables (two dependent
+      // lookups per char cost more than bank conflicts: [Ss]herlock 3.07 against 2.40 TB/s), the stride-1 table in 32
+      // copies, then one plain copy of it (large tables: thousands of states still fit in shared memory).  When find()
+      // needs the table-driven reverse pass, every layout that also holds the BACKWARDS rows comes first: the reverse pass
+      // then runs on the staged tile instead of global memory ((Holmes|Watson|...)+ find: 2.14 against 0.88 TB/s).
+      bool ok = false;
+      if (want_bwd) {
+        ok = lines8_layout(fwd_t, bwd_t, cw, false, img, b);
+        if (!ok) ok = lines8_layout(fwd_t, bwd_t, cw, true, img, b);
+        if (!ok && cw == 1) ok = lines8_layout_s1(fwd_t, bwd_t, 32, img, b);
+        if (!ok && cw == 1) ok = lines8_layout_s1(fwd_t, bwd_t, 1, img, b);
+      }
       if (!ok) ok = lines8_layout(fwd_t, nullptr, cw, false, img, b);
-      // unreplicated pair tables before the replicated stride-1 table: measured 3.07 against 2.40 TB/s on [Ss]herlock and
-      // 2.87 against 2.18 on Sherlock|Street (exp/large_table.py) - two dependent lookups per char cost more than bank conflicts
-      if (!ok) ok = want_bwd && lines8_layout(fwd_t, bwd_t, cw, true, img, b);
       if (!ok) ok = lines8_layout(fwd_t, nullptr, cw, true, img, b);
-      if (!ok && cw == 1) ok = want_bwd && lines8_layout_s1(fwd_t, bwd_t, 32, img, b);
       if (!ok && cw == 1) ok = lines8_layout_s1(fwd_t, nullptr, 32, img, b);
-      // large tables: one plain copy of the stride-1 table (thousands of states still fit in shared memory)
-      if (!ok && cw == 1) ok = want_bwd && lines8_layout_s1(fwd_t, bwd_t, 1, img, b);
       if (!ok && cw == 1) ok = lines8_layout_s1(fwd_t, nullptr, 1, img, b);
       if (!ok) continue;
       if (cudaMalloc(&b.dev, img.size()) != cudaSuccess ||
