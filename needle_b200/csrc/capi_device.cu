@@ -18,6 +18,7 @@
 #include "kernels/generic.cuh"
 #include "kernels/lines8.cuh"
 #include "kernels/long8.cuh"
+#include "kernels/layouts.h"
 #include "kernels/instances.h"
 #include "needle_b200.h"
 
