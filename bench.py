@@ -149,12 +149,32 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Multi-GPU runs: keep this rank (and the pinned buffers it allocates next) on the CPUs NVML reports as local to its
+    GPU, so that eight host->device streams do not all pull from one socket's memory.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1}
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return len(allowed)
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args, rank, local_rank, world):
     import torch
 
     import needle_b200 as nb
     from needle_b200 import _lib
 
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
@@ -319,7 +339,8 @@ def run_ours(args, rank, local_rank, world):
             "data": "synthetic",
             "config": {"workload": desc, "regex": regex, "mode": "find", "lines_per_gpu": n, "bytes_per_gpu_per_step": in_bytes,
                        "l2": f"inputs ({in_bytes / 1e6:.0f} MB per step) are larger than the 126 MB L2; no flush needed",
-                       "sharding": "contiguous line ranges per rank, table blob NCCL-broadcast once, no data-path collective"},
+                       "sharding": "contiguous line ranges per rank, table blob NCCL-broadcast once, no data-path collective",
+                       **({"host_binding": f"each rank bound to the {numa_cpus} CPUs local to its GPU (NVML affinity)"} if numa_cpus else {})},
             "matches_per_s": job_matches * args.steps / (ms * 1e-3),
             # equally spaced offsets are checked on the host (every one of them) and computed on the device instead of copied
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(e2e_bytes + (0 if fixed_len else off_h.nbytes)),
