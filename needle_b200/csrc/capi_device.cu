@@ -770,7 +770,8 @@ static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, in
   const Lines8Blob& qimg = p->q8[NDL_MODE_FIND];
   const Lines8Blob& img = qimg.ok && long8_kernel_for(qimg.char_mode) ? qimg : p->l8[NDL_MODE_FIND];
   // the chunk-parallel path is for the search phase (no match seen yet) of a pattern with a non-accepting root
-  const bool fast = char_width == 1 && !root_acc && img.ok && from < n && last_init == -1 && entry_state != dead;
+  const bool fast = char_width == 1 && !root_acc && img.ok && long8_kernel_for(img.char_mode) != nullptr && from < n && last_init == -1 &&
+                    entry_state != dead;
 
   if (!fast) {
     // plain sequential walk (accepting root, UTF-16, no shared-memory image, or continuing a match that is
