@@ -550,6 +550,22 @@ def test_swar_utf16_16bit_lanes(line_chars):
         assert_batch_equal(regex, 0, chars.view(np.uint8), offsets, cw=2)
 
 
+def test_utf16_high_byte_mode_with_from_offsets_and_long_lines():
+    """C5's regex (class from the high byte, table-driven reverse pass) with find(from, to) and with streamed long lines."""
+    rng = np.random.default_rng(77)
+    for lens in (rng.integers(0, 60, size=3000), rng.integers(150, 2500, size=300), np.full(500, 512)):
+        n = len(lens)
+        offsets = np.zeros(n + 1, dtype=np.uint64)
+        offsets[1:] = np.cumsum(lens)
+        total = int(offsets[-1])
+        chars = rng.integers(0x20, 0x400, size=total).astype(np.uint16)
+        hot = rng.random(total) < 0.3
+        chars[hot] = rng.integers(0x600, 0x700, size=int(hot.sum()))
+        frm = (rng.random(n) * (lens + 1)).astype(np.int32)
+        assert_batch_equal(workloads.REGEX["c5"], 0, chars.view(np.uint8), offsets, cw=2)
+        assert_batch_equal(workloads.REGEX["c5"], 0, chars.view(np.uint8), offsets, cw=2, from_=frm, modes=(2,))
+
+
 def test_swar_utf16_all_high_bytes():
     rng = np.random.default_rng(12)
     for line_chars in (32, 8, 128, 19):
