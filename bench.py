@@ -354,6 +354,7 @@ def run_ours(args, rank, local_rank, world):
                          "kernel": kernel_name(pat, cw), "kernel_ms": kernel_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": in_bytes,
                          "achieved_with_metadata": (in_bytes + 17 * n) / (kernel_ms * 1e-3) / 1e9,
+                         "frac_of_nominal_8tbs": achieved / 8000.0,
                          "note": "algorithmic bytes = haystack bytes only (SURVEY.md 8d); achieved_with_metadata adds the 8 B/line of offsets the "
                                  "launch must read and the 9 B/line of results it must write (the API's own traffic, also HBM-bound)"},
         }
