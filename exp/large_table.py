@@ -26,7 +26,8 @@ stream = torch.cuda.current_stream()
 name = nb._lib.lib().ndl_debug_kernel_name
 name.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
 name.restype = ctypes.c_char_p
-for regex in ("Holmes.{1,10}Watson|Watson.{1,10}Holmes", "Holmes.{0,25}Watson|Watson.{0,25}Holmes", "[Ss]herlock", "Sherlock|Street", "(Holmes|Watson|Sherlock|Street|dear|said)+"):
+for regex in ("Holmes.{1,10}Watson|Watson.{1,10}Holmes", "Holmes.{0,25}Watson|Watson.{0,25}Holmes", "[Ss]herlock", "Sherlock|Street", "(Holmes|Watson|Sherlock|Street|dear|said)+",
+              "Sherlock|Holmes|Watson|Irene|Adler|John|Baker"):
     pat = nb.Pattern(nb.compile_to_bytes(regex, 0), device=0)
     for mode in (2, 1):
         def step():

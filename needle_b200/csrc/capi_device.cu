@@ -375,8 +375,8 @@ const char* ndl_debug_kernel_name(const ndl_pattern* p, int mode, int char_width
            " compare planes, " + std::to_string(qb.replicated) + (cm_u16(qb.char_mode) ? " table copies of 16-bit entries" : " table copies") +
            (cm_wide(qb.char_mode) ? ", UTF-16 on 16-bit lanes>" : cm_hi(qb.char_mode) ? ", UTF-16 high byte>" : ">");
   } else if (lb.ok) {
-    static const char* kModes[] = {"pair table", "UTF-16 high byte", "UTF-16 mixed page", "stride-1 table"};
-    name = std::string("lines8_kernel<") + kModes[lb.char_mode & 3] + ">";
+    static const char* kModes[] = {"pair table", "UTF-16 high byte", "UTF-16 mixed page", "stride-1 table", "pair table, 16-bit entries"};
+    name = std::string("lines8_kernel<") + kModes[lb.char_mode <= 4 ? lb.char_mode : 0] + ">";
   } else {
     name = char_width == 1 ? "generic_batch_kernel<uint8_t>" : "generic_batch_kernel<uint16_t>";
   }
@@ -435,11 +435,13 @@ int ndl_pattern_create(const uint8_t* blob, size_t blob_len, int device, ndl_pat
       if (want_bwd) {
         ok = lines8_layout(fwd_t, bwd_t, cw, false, img, b);
         if (!ok) ok = lines8_layout(fwd_t, bwd_t, cw, true, img, b);
+        if (!ok && cw == 1) ok = lines8_layout(fwd_t, bwd_t, cw, true, img, b, true);
         if (!ok && cw == 1) ok = lines8_layout_s1(fwd_t, bwd_t, 32, img, b);
         if (!ok && cw == 1) ok = lines8_layout_s1(fwd_t, bwd_t, 1, img, b);
       }
       if (!ok) ok = lines8_layout(fwd_t, nullptr, cw, false, img, b);
       if (!ok) ok = lines8_layout(fwd_t, nullptr, cw, true, img, b);
+      if (!ok && cw == 1) ok = lines8_layout(fwd_t, nullptr, cw, true, img, b, true);
       if (!ok && cw == 1) ok = lines8_layout_s1(fwd_t, nullptr, 32, img, b);
       if (!ok && cw == 1) ok = lines8_layout_s1(fwd_t, nullptr, 1, img, b);
       if (!ok) continue;
@@ -786,7 +788,7 @@ static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, in
     // canonical state encoding of the image (long8.cuh): state id <-> table entry without flags / copy offset
     const bool swar = cm_is_swar(img.char_mode);
     const bool s1 = img.char_mode == kCmBytes1;
-    const uint32_t row_bytes = img.row_bytes;
+    const uint32_t row_bytes = img.char_mode == kCmBytesH ? img.row_bytes / 2 : img.row_bytes;  // what an entry holds per row
     const uint32_t eb = swar && cm_u16(img.char_mode) ? 2u : 4u;
     const uint32_t w_rows = swar ? 128u / eb / static_cast<uint32_t>(img.replicated) : 1u;
     auto enc = [&](int32_t state) -> uint32_t {

@@ -21,7 +21,8 @@ namespace ndl {
 // Returns false when the class map has no supported char mode or the pair tables do not fit (the generic
 // kernel handles the pattern then).
 inline bool lines8_layout(const HostDeviceTable& f, const HostDeviceTable* b, int char_width, bool allow_unreplicated,
-                          std::vector<uint8_t>& img, Lines8Blob& meta) {
+                          std::vector<uint8_t>& img, Lines8Blob& meta, bool entries16 = false) {
+  // entries16 (byte haystacks, one plain copy): 16-bit entries = byte offset of the target row / 2 | flags << 14 (kCmBytesH)
   using Key = std::pair<int, int>;
   auto key_of = [&](int c) { return Key{f.cmap[c], b ? b->cmap[c] : 0}; };
   Key slot_key[256];
@@ -69,13 +70,17 @@ inline bool lines8_layout(const HostDeviceTable& f, const HostDeviceTable* b, in
   const int rows_f = f.n_states + 1, rows_b = b ? b->n_states + 1 : 0;
   const long pairs = static_cast<long>(rows_f + rows_b) * C * C;
   int R;
-  if (pairs * 128 <= static_cast<long>(kL8MaxTransBytes))
-    R = 32;
-  else if (allow_unreplicated && pairs * 4 <= static_cast<long>(kL8MaxTransBytes))
+  if (entries16) {
+    if (char_mode != kCmBytes || !allow_unreplicated || pairs * 2 > static_cast<long>(kL8MaxTransBytes) || pairs * 2 > 0x8000) return false;
     R = 1;
-  else
+  } else if (pairs * 128 <= static_cast<long>(kL8MaxTransBytes)) {
+    R = 32;
+  } else if (allow_unreplicated && pairs * 4 <= static_cast<long>(kL8MaxTransBytes)) {
+    R = 1;
+  } else {
     return false;
-  const uint32_t col_bytes = 4u * R;
+  }
+  const uint32_t col_bytes = entries16 ? 2u : 4u * R;
   const uint32_t row_bytes = static_cast<uint32_t>(C) * C * col_bytes;
   const uint32_t trans_bytes = (static_cast<uint32_t>(rows_f + rows_b) * row_bytes + 15) & ~15u;
   img.assign(kL8CmapBytes + trans_bytes, 0);
@@ -96,26 +101,33 @@ inline bool lines8_layout(const HostDeviceTable& f, const HostDeviceTable* b, in
         for (int c2 = 0; c2 < C; c2++) {
           const int k2 = backward ? col_classes[c2].second : col_classes[c2].first;
           const int s2 = t.trans[static_cast<size_t>(s1) * t.n_classes + k2];
+          const uint32_t at = kL8CmapBytes + static_cast<uint32_t>(row0 + s) * row_bytes + (static_cast<uint32_t>(c1) * C + c2) * col_bytes;
+          if (entries16) {
+            const uint16_t e16 = static_cast<uint16_t>((static_cast<uint32_t>(row0 + s2) * row_bytes) >> 1 | (t.accept[s1] ? 0x8000u : 0) |
+                                                       (t.accept[s2] ? 0x4000u : 0));
+            std::memcpy(img.data() + at, &e16, 2);
+            continue;
+          }
           const uint32_t e = static_cast<uint32_t>(row0 + s2) * row_bytes | (t.accept[s1] ? 0x80000000u : 0) | (t.accept[s2] ? 0x40000000u : 0);
-          for (int lane = 0; lane < R; lane++)
-            put(kL8CmapBytes + static_cast<uint32_t>(row0 + s) * row_bytes + (static_cast<uint32_t>(c1) * C + c2) * col_bytes + lane * 4, e);
+          for (int lane = 0; lane < R; lane++) put(at + lane * 4, e);
         }
       }
   };
   emit(f, 0, false);
+  const uint32_t state_unit = entries16 ? row_bytes / 2 : row_bytes;  // what a table entry holds per row
   meta.root_entry = 0;  // forward root = row 0
-  meta.fwd_dead = static_cast<uint32_t>(f.n_states) * row_bytes;
+  meta.fwd_dead = static_cast<uint32_t>(f.n_states) * state_unit;
   meta.has_bwd = b != nullptr;
   if (b) {
     emit(*b, rows_f, true);
-    meta.bwd_root = static_cast<uint32_t>(rows_f) * row_bytes;
-    meta.bwd_dead = static_cast<uint32_t>(rows_f + b->n_states) * row_bytes;
+    meta.bwd_root = static_cast<uint32_t>(rows_f) * state_unit;
+    meta.bwd_dead = static_cast<uint32_t>(rows_f + b->n_states) * state_unit;
   }
   meta.trans_bytes = trans_bytes;
   meta.replicated = R;
   meta.n_cols = C;
   meta.row_bytes = row_bytes;
-  meta.char_mode = char_mode;
+  meta.char_mode = entries16 ? static_cast<int>(kCmBytesH) : char_mode;
   meta.mixed_page = mixed_page < 0 ? 0 : mixed_page;
   meta.ua = static_cast<uint32_t>(col_uniform) * C * col_bytes;
   meta.ub = kL8AbsTrans + static_cast<uint32_t>(col_uniform) * col_bytes;  // + lane*4 in the kernel when replicated

@@ -90,7 +90,9 @@ constexpr uint32_t kS1UpperLo = kS1AbsTrans + kS1MaxTransBytes;  // 0x28800
 //             select replaces the looked-up value by the common class when the high byte is another page.
 // Any other UTF-16 class map is left to the generic kernel.
 //   kCmBytes1 char_width 1, ONE char per step over the S1 layout (see kS1* above).
-enum { kCmBytes = 0, kCmHi = 1, kCmMixed = 2, kCmBytes1 = 3 };
+//   kCmBytesH char_width 1, as kCmBytes with one plain copy of the pair table in 16-bit entries (byte offset of the
+//             target row / 2 | accept flags << 14): twice the automaton in the same 32 KB - keyword lists and the like.
+enum { kCmBytes = 0, kCmHi = 1, kCmMixed = 2, kCmBytes1 = 3, kCmBytesH = 4 };
 // SWAR modes ("Q" layout, linesq_kernel): no class map in shared memory at all.  The class of a char comes
 // from packed compares (swar_plan.h), the automaton is stepped K = 2 or 4 chars per transition lookup, and
 // the column offset of a K-char group is a dot product (IDP.4A) of the compare planes with per-position
@@ -231,9 +233,10 @@ struct L8Ctx {
 template <int CM>
 struct L8Enc {
   static constexpr uint32_t kStateMask =
-      CM == kCmBytes1 ? 0x7fffu : cm_u16(CM) ? (0xffffu >> cm_k(CM)) : cm_is_swar(CM) ? (0xffffffffu >> cm_k(CM)) : kL8FlagMask;
+      CM == kCmBytes1 ? 0x7fffu : CM == kCmBytesH ? 0x3fffu : cm_u16(CM) ? (0xffffu >> cm_k(CM)) : cm_is_swar(CM) ? (0xffffffffu >> cm_k(CM)) : kL8FlagMask;
   // accept flag of the LAST char of a step (kCmBytes1 entries are sign-extended, so bit 30 works there too)
-  static constexpr uint32_t kTailFlag = cm_u16(CM) ? (0x8000u >> (cm_k(CM) - 1)) : cm_is_swar(CM) ? (0x80000000u >> (cm_k(CM) - 1)) : 0x40000000u;
+  static constexpr uint32_t kTailFlag =
+      CM == kCmBytesH ? 0x4000u : cm_u16(CM) ? (0x8000u >> (cm_k(CM) - 1)) : cm_is_swar(CM) ? (0x80000000u >> (cm_k(CM) - 1)) : 0x40000000u;
 };
 
 // One 2-char step.  KA / KB: byte index (within the 32-bit word) that selects the class-map slot of the
@@ -246,12 +249,19 @@ __device__ __forceinline__ void l8_step2(uint32_t word, const L8Ctx& cx, uint32_
     ca = ((word & (0xffu << (8 * HA))) == (HA == 1 ? cx.page1 : cx.page3)) ? ca : cx.ua;
     cb = ((word & (0xffu << (8 * HB))) == (HB == 1 ? cx.page1 : cx.page3)) ? cb : cx.ub;
   }
-  if (CM != kCmBytes) {  // the char in the low (H == 1) / high (H == 3) half of the word is U+FFFF
+  if (CM != kCmBytes && CM != kCmBytesH) {  // the char in the low (H == 1) / high (H == 3) half of the word is U+FFFF
     ca = (HA == 1 ? (word & 0xffffu) == 0xffffu : word >= 0xffff0000u) ? cx.xa : ca;
     cb = (HB == 1 ? (word & 0xffffu) == 0xffffu : word >= 0xffff0000u) ? cx.xb : cb;
   }
-  e = lds_tab((e & kL8FlagMask) + ca + cb);
-  mask = __funnelshift_l(e, mask, 2);  // mask = mask << 2 | accept(1st) << 1 | accept(2nd)
+  if (CM == kCmBytesH) {  // 16-bit entries: row offset / 2 in the low 14 bits, the two flags above
+    uint32_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"((e & 0x3fffu) * 2u + (ca + cb)));
+    e = v;
+    mask = __funnelshift_l(e * 0x10000u, mask, 2);
+  } else {
+    e = lds_tab((e & kL8FlagMask) + ca + cb);
+    mask = __funnelshift_l(e, mask, 2);  // mask = mask << 2 | accept(1st) << 1 | accept(2nd)
+  }
 }
 
 __device__ __forceinline__ int32_t lds_tab_s16(uint32_t addr) {
@@ -277,7 +287,7 @@ __device__ __forceinline__ void l8_word(uint32_t w, const L8Ctx& cx, uint32_t& e
     l8_step1<1>(w, cx, e, mask);
     l8_step1<2>(w, cx, e, mask);
     l8_step1<3>(w, cx, e, mask);
-  } else if (CM == kCmBytes) {
+  } else if (CM == kCmBytes || CM == kCmBytesH) {
     l8_step2<CM, 0, 1, 0, 0>(w, cx, e, mask);
     l8_step2<CM, 2, 3, 0, 0>(w, cx, e, mask);
   } else if (CM == kCmHi) {
@@ -293,7 +303,7 @@ __device__ __forceinline__ void l8_word_rev(uint32_t w, const L8Ctx& cx, uint32_
     l8_step1<2>(w, cx, e, mask);
     l8_step1<1>(w, cx, e, mask);
     l8_step1<0>(w, cx, e, mask);
-  } else if (CM == kCmBytes) {
+  } else if (CM == kCmBytes || CM == kCmBytesH) {
     l8_step2<CM, 3, 2, 0, 0>(w, cx, e, mask);
     l8_step2<CM, 1, 0, 0, 0>(w, cx, e, mask);
   } else if (CM == kCmHi) {
@@ -304,7 +314,7 @@ __device__ __forceinline__ void l8_word_rev(uint32_t w, const L8Ctx& cx, uint32_
 }
 template <int CM>
 struct L8Chars {
-  static constexpr int kBytes = (CM == kCmBytes || CM == kCmBytes1 || (cm_is_swar(CM) && !cm_hi(CM) && !cm_wide(CM))) ? 1 : 2;   // bytes per char
+  static constexpr int kBytes = (CM == kCmBytes || CM == kCmBytes1 || CM == kCmBytesH || (cm_is_swar(CM) && !cm_hi(CM) && !cm_wide(CM))) ? 1 : 2;   // bytes per char
   static constexpr int kPerChunk = 16 / kBytes;           // chars (= accept bits) per 16-byte chunk
 };
 
@@ -1085,7 +1095,7 @@ __global__ void __launch_bounds__(kL8Threads, 1) lines8_kernel(const Lines8Param
   }
 
   // --- line geometry: byte length from the first two offsets (uniform); every tile re-checks its own lines
-  const uint32_t char_bytes = (p.char_mode == kCmBytes || p.char_mode == kCmBytes1) ? 1u : 2u;
+  const uint32_t char_bytes = (p.char_mode == kCmBytes || p.char_mode == kCmBytes1 || p.char_mode == kCmBytesH) ? 1u : 2u;
   const uint64_t l_chars = batch_off(g, 1) - batch_off(g, 0);
   const uint64_t L64 = l_chars * char_bytes;
   int log2cpl = -1;
@@ -1126,7 +1136,8 @@ __global__ void __launch_bounds__(kL8Threads, 1) lines8_kernel(const Lines8Param
   cx.bwd_root = p.bwd_root;
   cx.bwd_dead = p.bwd_dead;
   cx.fwd_dead = p.fwd_dead;
-  if (p.char_mode == kCmBytes1) l8_dispatch<kCmBytes1>(p, cx, log2cpl, buf0, buf1, lane, warp_global, n_warps);
+  if (p.char_mode == kCmBytesH) l8_dispatch<kCmBytesH>(p, cx, log2cpl, buf0, buf1, lane, warp_global, n_warps);
+  else if (p.char_mode == kCmBytes1) l8_dispatch<kCmBytes1>(p, cx, log2cpl, buf0, buf1, lane, warp_global, n_warps);
   else if (p.char_mode == kCmBytes) l8_dispatch<kCmBytes>(p, cx, log2cpl, buf0, buf1, lane, warp_global, n_warps);
   else if (p.char_mode == kCmHi) l8_dispatch<kCmHi>(p, cx, log2cpl, buf0, buf1, lane, warp_global, n_warps);
   else l8_dispatch<kCmMixed>(p, cx, log2cpl, buf0, buf1, lane, warp_global, n_warps);

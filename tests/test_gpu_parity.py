@@ -485,6 +485,8 @@ def test_expected_kernels_are_selected():
     assert fp == {"char_mode": 64 | 16 | 8 | 2, "replicated": 16, "has_bwd": 0, "n_cols": 3}  # ASCII pattern over UTF-16: 16-bit lanes
     fp = fast_path(pair(workloads.REGEX["c3"])[0], 2, 2)
     assert fp["char_mode"] == 2  # e-mail regex over UTF-16: no compare plan, one mixed page (lines8)
+    fp = fast_path(pair("Sherlock|Holmes|Watson|Irene|Adler|John|Baker")[0], 1, 1)
+    assert fp["char_mode"] == 4 and fp["replicated"] == 1  # keyword list, containedIn: one plain copy of the pair table in 16-bit entries
     assert fast_path(pair("[a-bα-ω]+")[0], 2, 2)["char_mode"] & 64  # two mixed pages: no lines8 mode, but two ranges on 16-bit lanes
     assert fast_path(pair("[a-bα-ωа-я一-龥]+@")[0], 2, 2) is None  # four mixed pages, five ranges: generic kernel
     fp = fast_path(pair("Holmes.{1,10}Watson|Watson.{1,10}Holmes")[0], 2, 1)
