@@ -32,7 +32,7 @@ SYMBOLS = (
     "ndl_pattern_destroy", "ndl_match_batch", "ndl_find_long", "ndl_last_error", "ndl_version",
     "ndl_device_count", "ndl_kernel_launches", "ndl_pattern_device", "ndl_find_long_from", "ndl_forwards_state_count",
     "ndl_find_long_back", "ndl_backwards_state_count", "ndl_backwards_root_accepting", "ndl_reverse_mode", "ndl_min_length",
-    "ndl_find_all_batch", "ndl_match_lines",
+    "ndl_find_all_batch", "ndl_match_lines", "ndl_pattern_device_count", "ndl_host_alloc", "ndl_host_free",
 )
 
 _lib = None
@@ -89,6 +89,12 @@ def lib():
     L.ndl_kernel_launches.restype = ctypes.c_uint64
     L.ndl_pattern_device.argtypes = [ctypes.c_void_p]
     L.ndl_pattern_device.restype = ctypes.c_int
+    L.ndl_pattern_device_count.argtypes = [ctypes.c_void_p]
+    L.ndl_pattern_device_count.restype = ctypes.c_int
+    L.ndl_host_alloc.argtypes = [ctypes.c_size_t]
+    L.ndl_host_alloc.restype = ctypes.c_void_p
+    L.ndl_host_free.argtypes = [ctypes.c_void_p]
+    L.ndl_host_free.restype = None
     _ = (i32p, u64p)
     _lib = L
     return L

@@ -23,6 +23,31 @@ class Table:
 
 
 @dataclass
+class Accel:
+    """The accelerator record of a version-2 blob (csrc/host/pattern.h Accel; DFAClassBuilder.java:365-429)."""
+    present: bool = False
+    use_prefix: bool = False
+    use_suffix: bool = False
+    use_infixes: bool = False
+    use_max_start: bool = False
+    can_seek_for_predicate: bool = False
+    has_first_byte_mask: bool = False
+    byte_check_first_char: bool = False
+    post_prefix_accepting: bool = False
+    follow_accepting: bool = False
+    inner_must_call_was_accepted: bool = False
+    post_prefix_state: int = 0
+    follow_state: int = 0
+    pred_kind: int = 0
+    pred_a: int = 0
+    pred_b: int = 0
+    prefix: str = ""
+    suffix: str = ""
+    infix: str = ""
+    first_byte_mask: List[int] = field(default_factory=list)  # the indices (0..128) that are set
+
+
+@dataclass
 class Blob:
     version: int
     flags: int
@@ -34,6 +59,7 @@ class Blob:
     reverse_char: int
     class_map: np.ndarray  # uint16[65536]
     tables: List[Table] = field(default_factory=list)
+    accel: Accel = field(default_factory=Accel)
 
 
 def _fnv1a(b: bytes) -> int:
@@ -66,4 +92,18 @@ def parse_blob(b: bytes) -> Blob:
         ent = np.frombuffer(b, dtype="<i2", count=n_states * stride, offset=pos).reshape(n_states, stride).copy()
         pos = (pos + 2 * n_states * stride + 3) & ~3
         out.tables.append(Table(n_states, width, max_char, acc, ent))
+    if version >= 2:
+        magic2, f, pps, fs, pk, pa, pb = struct.unpack_from("<IIiiiii", b, pos)
+        if magic2 != 0x4C434341:
+            raise ValueError("accelerator record missing")
+        pos += 28
+        strs = []
+        for _ in range(3):
+            (n,) = struct.unpack_from("<I", b, pos)
+            pos += 4
+            strs.append(b[pos:pos + 2 * n].decode("utf-16-le", "surrogatepass"))
+            pos = (pos + 2 * n + 3) & ~3
+        mask = [i for i in range(129) if b[pos + i]]
+        out.accel = Accel(bool(f & 1024), bool(f & 1), bool(f & 2), bool(f & 4), bool(f & 8), bool(f & 16), bool(f & 32), bool(f & 64),
+                          bool(f & 128), bool(f & 256), bool(f & 512), pps, fs, pk, pa, pb, strs[0], strs[1], strs[2], mask)
     return out

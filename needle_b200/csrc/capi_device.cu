@@ -3,18 +3,22 @@
 // There is deliberately no CPU matcher behind these entry points: without a usable CUDA device they
 // return NDL_ECUDA.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #define NDL_MAIN_TU  // this file compiles the non-template kernels of the shared headers
 #include "capi_internal.h"
 #include "device_image.h"
 #include "host/pattern.h"
+#include "host_chunks.h"
+#include "host_staging.h"
 #include "kernels/generic.cuh"
 #include "kernels/lines8.cuh"
 #include "kernels/long8.cuh"
@@ -33,9 +37,33 @@ static std::atomic<uint64_t> g_launches{0};
       return fail(NDL_ECUDA, std::string(#expr) + " failed: " + cudaGetErrorString(_e));           \
   } while (0)
 
+// Makes `device` current for the scope and restores the caller's device afterwards: a host that drives several
+// GPUs from one thread (PyTorch, the multi-device pattern below) must not find its current device switched.
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+      cudaGetLastError();
+      prev = -1;
+    }
+    if (prev != device) err = cudaSetDevice(device);
+    else prev = -1;  // nothing to restore
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define NDL_DEVICE(guard)                                                                                        \
+  do {                                                                                                           \
+    if ((guard).err != cudaSuccess) return fail(NDL_ECUDA, std::string("cudaSetDevice failed: ") + cudaGetErrorString((guard).err)); \
+  } while (0)
+
 struct DeviceTableStorage {
   HostDeviceTable host;
-  uint16_t* cmap = nullptr;
+  uint16_t* cmap = nullptr;  // (pointers into the pattern's device arena)
   uint16_t* trans = nullptr;
   uint8_t* accept = nullptr;
   DevTable view() const {
@@ -50,7 +78,8 @@ struct DeviceTableStorage {
   }
 };
 
-// Grow-only device staging for NDL_MEM_HOST calls.
+// Grow-only staging for NDL_MEM_HOST calls: the device side, and - for callers whose buffers are pageable - a pinned
+// bounce ring for the input and pinned mirrors of the result arrays (an asynchronous DMA needs page-locked memory).
 struct Workspace {
   void* data = nullptr;
   size_t data_cap = 0;
@@ -60,12 +89,53 @@ struct Workspace {
   int32_t* start = nullptr;
   int32_t* end = nullptr;
   size_t n_cap = 0;
+  // ndl_find_all_batch on host buffers
+  uint32_t* counts = nullptr;
+  uint64_t* match_offsets = nullptr;
+  size_t counts_cap = 0;
+  int32_t* all_starts = nullptr;
+  int32_t* all_ends = nullptr;
+  size_t all_cap = 0;
   // ndl_find_long: per-tile seam arrays and the scratch record
   uint32_t* seam_guess = nullptr;
   uint32_t* seam_exit = nullptr;
   uint32_t* seam_acc = nullptr;
   size_t seam_cap = 0;
   void* long_scratch = nullptr;
+  // pageable callers
+  static constexpr int kRing = 3;
+  static constexpr size_t kRingBytes = 32u << 20;
+  uint8_t* ring[kRing] = {};
+  cudaEvent_t ring_done[kRing] = {};
+  int ring_next = 0;
+  uint8_t* h_matched = nullptr;  // pinned mirrors of matched / start / end
+  int32_t* h_start = nullptr;
+  int32_t* h_end = nullptr;
+  size_t h_cap = 0;
+};
+
+// Everything a pattern puts on a device lives in ONE allocation ("arena"): the four generic tables and the up to twelve
+// shared-memory images.  One upload per device - or, for a multi-device pattern, one upload to the first device and one
+// NCCL broadcast of the arena to the others.
+struct Arena {
+  std::vector<uint8_t> host;
+  size_t add(const void* src, size_t bytes) {
+    const size_t off = (host.size() + 255) & ~static_cast<size_t>(255);
+    host.resize(off + bytes);
+    if (bytes) std::memcpy(host.data() + off, src, bytes);
+    return off;
+  }
+};
+constexpr size_t kNoImage = ~static_cast<size_t>(0);
+
+// Host half of a pattern: built once from the blob, shared by the replicas of a multi-device pattern.
+struct HostPattern {
+  CompiledPattern cp;
+  HostDeviceTable tables[4];
+  size_t off_cmap[4], off_trans[4], off_accept[4];
+  Lines8Blob l8[3], l16[3], q8[3], q16[3];  // metadata (dev == nullptr); ok = an image exists in the arena
+  size_t off_l8[3], off_l16[3], off_q8[3], off_q16[3];
+  Arena arena;
 };
 
 }  // namespace ndl
@@ -74,64 +144,62 @@ using namespace ndl;
 
 struct ndl_pattern {
   CompiledPattern cp;
-  int device = 0;
+  int device = 0;  // -1: multi-device pattern, `replicas` holds one pattern per GPU and this object only routes
   int sm_count = 0;
   DeviceTableStorage tables[4];
   Lines8Blob l8[3];   // per mode: shared-memory image of the lines8 kernel for byte haystacks
   Lines8Blob l16[3];  // per mode: same for UTF-16 haystacks (when the class map has a supported char mode)
   Lines8Blob q8[3];   // per mode: SWAR image (linesq_kernel) for byte haystacks, when the class map has a plan
   Lines8Blob q16[3];  // per mode: same for UTF-16 haystacks
+  uint8_t* arena = nullptr;
+  size_t arena_bytes = 0;
   std::mutex ws_mutex;
   Workspace ws;
   bool long8_ready = false;  // long8_kernel's shared-memory attribute is set
   // host-buffer calls are pipelined in chunks: H2D on s_h2d, kernels on the caller's stream, D2H on s_d2h
   static constexpr int kMaxChunks = 16;
-  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_own = nullptr;
   cudaEvent_t ev_start = nullptr, ev_h2d[kMaxChunks] = {}, ev_kernel[kMaxChunks] = {};
+  std::vector<ndl_pattern*> replicas;
 };
 
 namespace ndl {
 
-static int upload_table(DeviceTableStorage& t) {
-  NDL_CUDA(cudaMalloc(&t.cmap, t.host.cmap.size() * sizeof(uint16_t)));
-  NDL_CUDA(cudaMalloc(&t.trans, t.host.trans.size() * sizeof(uint16_t)));
-  NDL_CUDA(cudaMalloc(&t.accept, t.host.accept.size()));
-  NDL_CUDA(cudaMemcpy(t.cmap, t.host.cmap.data(), t.host.cmap.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-  NDL_CUDA(cudaMemcpy(t.trans, t.host.trans.data(), t.host.trans.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-  NDL_CUDA(cudaMemcpy(t.accept, t.host.accept.data(), t.host.accept.size(), cudaMemcpyHostToDevice));
-  return NDL_OK;
-}
-
 static void free_pattern(ndl_pattern* p) {
   if (!p) return;
-  int prev = 0;
-  cudaGetDevice(&prev);
-  cudaSetDevice(p->device);
-  for (auto& t : p->tables) {
-    cudaFree(t.cmap);
-    cudaFree(t.trans);
-    cudaFree(t.accept);
+  for (ndl_pattern* r : p->replicas) free_pattern(r);
+  if (p->device >= 0) {
+    DeviceGuard guard(p->device);
+    cudaFree(p->arena);
+    if (p->s_h2d) cudaStreamDestroy(p->s_h2d);
+    if (p->s_d2h) cudaStreamDestroy(p->s_d2h);
+    if (p->s_own) cudaStreamDestroy(p->s_own);
+    if (p->ev_start) cudaEventDestroy(p->ev_start);
+    for (auto& e : p->ev_h2d) if (e) cudaEventDestroy(e);
+    for (auto& e : p->ev_kernel) if (e) cudaEventDestroy(e);
+    Workspace& ws = p->ws;
+    cudaFree(ws.data);
+    cudaFree(ws.offsets);
+    cudaFree(ws.from);
+    cudaFree(ws.matched);
+    cudaFree(ws.start);
+    cudaFree(ws.end);
+    cudaFree(ws.counts);
+    cudaFree(ws.match_offsets);
+    cudaFree(ws.all_starts);
+    cudaFree(ws.all_ends);
+    cudaFree(ws.seam_guess);
+    cudaFree(ws.seam_exit);
+    cudaFree(ws.seam_acc);
+    cudaFree(ws.long_scratch);
+    for (int k = 0; k < Workspace::kRing; k++) {
+      if (ws.ring[k]) cudaFreeHost(ws.ring[k]);
+      if (ws.ring_done[k]) cudaEventDestroy(ws.ring_done[k]);
+    }
+    if (ws.h_matched) cudaFreeHost(ws.h_matched);
+    if (ws.h_start) cudaFreeHost(ws.h_start);
+    if (ws.h_end) cudaFreeHost(ws.h_end);
   }
-  for (auto& b : p->l8) cudaFree(b.dev);
-  for (auto& b : p->l16) cudaFree(b.dev);
-  for (auto& b : p->q8) cudaFree(b.dev);
-  for (auto& b : p->q16) cudaFree(b.dev);
-  if (p->s_h2d) cudaStreamDestroy(p->s_h2d);
-  if (p->s_d2h) cudaStreamDestroy(p->s_d2h);
-  if (p->ev_start) cudaEventDestroy(p->ev_start);
-  for (auto& e : p->ev_h2d) if (e) cudaEventDestroy(e);
-  for (auto& e : p->ev_kernel) if (e) cudaEventDestroy(e);
-  cudaFree(p->ws.data);
-  cudaFree(p->ws.offsets);
-  cudaFree(p->ws.from);
-  cudaFree(p->ws.matched);
-  cudaFree(p->ws.start);
-  cudaFree(p->ws.end);
-  cudaFree(p->ws.seam_guess);
-  cudaFree(p->ws.seam_exit);
-  cudaFree(p->ws.seam_acc);
-  cudaFree(p->ws.long_scratch);
-  cudaSetDevice(prev);
   delete p;
 }
 
@@ -156,6 +224,60 @@ static int ensure_workspace(Workspace& ws, size_t data_bytes, uint64_t n, bool w
     NDL_CUDA(cudaMalloc(&ws.start, cap * sizeof(int32_t)));
     NDL_CUDA(cudaMalloc(&ws.end, cap * sizeof(int32_t)));
     ws.n_cap = cap;
+  }
+  return NDL_OK;
+}
+
+// Is `p` page-locked (cudaHostAlloc / cudaHostRegister / managed) - i.e. can it be the end of an asynchronous DMA?
+static bool host_is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+static int ensure_ring(Workspace& ws) {
+  for (int k = 0; k < Workspace::kRing; k++) {
+    if (!ws.ring[k]) NDL_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ws.ring[k]), Workspace::kRingBytes, cudaHostAllocDefault));
+    if (!ws.ring_done[k]) NDL_CUDA(cudaEventCreateWithFlags(&ws.ring_done[k], cudaEventDisableTiming));
+  }
+  return NDL_OK;
+}
+
+static int ensure_result_mirrors(Workspace& ws, uint64_t n, bool want_pos) {
+  if (n > ws.h_cap || (want_pos && !ws.h_start)) {
+    if (ws.h_matched) cudaFreeHost(ws.h_matched);
+    if (ws.h_start) cudaFreeHost(ws.h_start);
+    if (ws.h_end) cudaFreeHost(ws.h_end);
+    ws.h_matched = nullptr; ws.h_start = nullptr; ws.h_end = nullptr;
+    ws.h_cap = 0;
+    const size_t cap = n + n / 8 + 16;
+    NDL_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ws.h_matched), cap, cudaHostAllocDefault));
+    NDL_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ws.h_start), cap * sizeof(int32_t), cudaHostAllocDefault));
+    NDL_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ws.h_end), cap * sizeof(int32_t), cudaHostAllocDefault));
+    ws.h_cap = cap;
+  }
+  return NDL_OK;
+}
+
+// Host -> device copy on `s`.  Pinned source: one asynchronous copy.  Pageable source: pieces of it are copied into
+// the pinned ring by the copy threads and sent from there, so the link stays busy while the next piece is being staged.
+static int h2d_copy(Workspace& ws, void* dst, const void* src, size_t bytes, bool pinned, cudaStream_t s) {
+  if (bytes == 0) return NDL_OK;
+  if (pinned) {
+    NDL_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+    return NDL_OK;
+  }
+  for (size_t off = 0; off < bytes; off += Workspace::kRingBytes) {
+    const size_t piece = bytes - off < Workspace::kRingBytes ? bytes - off : Workspace::kRingBytes;
+    const int slot = ws.ring_next;
+    ws.ring_next = (ws.ring_next + 1) % Workspace::kRing;
+    NDL_CUDA(cudaEventSynchronize(ws.ring_done[slot]));  // the copy that last used this slot has left it
+    CopyPool::instance().copy(ws.ring[slot], static_cast<const uint8_t*>(src) + off, piece);
+    NDL_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(dst) + off, ws.ring[slot], piece, cudaMemcpyHostToDevice, s));
+    NDL_CUDA(cudaEventRecord(ws.ring_done[slot], s));
   }
   return NDL_OK;
 }
@@ -383,12 +505,192 @@ const char* ndl_debug_kernel_name(const ndl_pattern* p, int mode, int char_width
   return name.c_str();
 }
 
+}  // extern "C"
+
+namespace ndl {
+
+// Blob -> host half of a pattern: the generic tables and every shared-memory image, laid out in one arena.
+static void build_host_pattern(HostPattern& hp) {
+  for (int k = 0; k < 4; k++) {
+    hp.tables[k] = build_device_table(hp.cp, k);
+    const HostDeviceTable& t = hp.tables[k];
+    hp.off_cmap[k] = hp.arena.add(t.cmap.data(), t.cmap.size() * sizeof(uint16_t));
+    hp.off_trans[k] = hp.arena.add(t.trans.data(), t.trans.size() * sizeof(uint16_t));
+    hp.off_accept[k] = hp.arena.add(t.accept.data(), t.accept.size());
+  }
+  for (int cw = 1; cw <= 2; cw++)
+    for (int mode = 0; mode < 3; mode++) {
+      const HostDeviceTable& fwd_t = hp.tables[mode == NDL_MODE_FIND ? kForwards : mode];
+      const bool want_bwd = mode == NDL_MODE_FIND && hp.cp.reverse_mode == kReverseTable;
+      const HostDeviceTable* bwd_t = want_bwd ? &hp.tables[kBackwards] : nullptr;
+      std::vector<uint8_t> img;
+      // --- "L" image (class map in shared memory, lines8_kernel)
+      // Preference (measured, exp/large_table.py): bank-replicated pair tables, unreplicated pair tables (two dependent
+      // lookups per char cost more than bank conflicts: [Ss]herlock 3.07 against 2.40 TB/s), the stride-1 table in 32
+      // copies, then one plain copy of it (large tables: thousands of states still fit in shared memory).  When find()
+      // needs the table-driven reverse pass, every layout that also holds the BACKWARDS rows comes first: the reverse pass
+      // then runs on the staged tile instead of global memory ((Holmes|Watson|...)+ find: 2.14 against 0.88 TB/s).
+      {
+        Lines8Blob& b = cw == 1 ? hp.l8[mode] : hp.l16[mode];
+        bool ok = false;
+        if (want_bwd) {
+          ok = lines8_layout(fwd_t, bwd_t, cw, false, img, b);
+          if (!ok) ok = lines8_layout(fwd_t, bwd_t, cw, true, img, b);
+          if (!ok && cw == 1) ok = lines8_layout(fwd_t, bwd_t, cw, true, img, b, true);
+          if (!ok && cw == 1) ok = lines8_layout_s1(fwd_t, bwd_t, 32, img, b);
+          if (!ok && cw == 1) ok = lines8_layout_s1(fwd_t, bwd_t, 1, img, b);
+        }
+        if (!ok) ok = lines8_layout(fwd_t, nullptr, cw, false, img, b);
+        if (!ok) ok = lines8_layout(fwd_t, nullptr, cw, true, img, b);
+        if (!ok && cw == 1) ok = lines8_layout(fwd_t, nullptr, cw, true, img, b, true);
+        if (!ok && cw == 1) ok = lines8_layout_s1(fwd_t, nullptr, 32, img, b);
+        if (!ok && cw == 1) ok = lines8_layout_s1(fwd_t, nullptr, 1, img, b);
+        b.ok = ok;
+        b.dev = nullptr;
+        (cw == 1 ? hp.off_l8[mode] : hp.off_l16[mode]) = ok ? hp.arena.add(img.data(), img.size()) : kNoImage;
+      }
+      // --- "Q" image (packed-compare classifier, linesq_kernel), where the class map has a plan
+      {
+        Lines8Blob b;
+        bool ok = want_bwd && linesq_layout(fwd_t, bwd_t, cw, img, b);
+        if (!ok) ok = linesq_layout(fwd_t, nullptr, cw, img, b);
+        if (ok && !linesq_kernel_for(b.char_mode)) ok = false;
+        b.ok = ok;
+        b.dev = nullptr;
+        (cw == 1 ? hp.q8[mode] : hp.q16[mode]) = b;
+        (cw == 1 ? hp.off_q8[mode] : hp.off_q16[mode]) = ok ? hp.arena.add(img.data(), img.size()) : kNoImage;
+      }
+    }
+}
+
+// Device half on `device`: allocates the arena (its content arrives by upload or broadcast), sets the kernel attributes.
+static int instantiate_pattern(const HostPattern& hp, int device, ndl_pattern** out) {
+  DeviceGuard guard(device);
+  NDL_DEVICE(guard);
+  cudaDeviceProp prop;
+  NDL_CUDA(cudaGetDeviceProperties(&prop, device));
+  ndl_pattern* p = new ndl_pattern();
+  p->cp = hp.cp;
+  p->device = device;
+  p->sm_count = prop.multiProcessorCount;
+  p->arena_bytes = hp.arena.host.size();
+  if (cudaMalloc(&p->arena, p->arena_bytes) != cudaSuccess) {
+    cudaGetLastError();
+    delete p;
+    return fail(NDL_ECUDA, "cudaMalloc of the pattern's device arena failed");
+  }
+  for (int k = 0; k < 4; k++) {
+    p->tables[k].host = hp.tables[k];
+    p->tables[k].cmap = reinterpret_cast<uint16_t*>(p->arena + hp.off_cmap[k]);
+    p->tables[k].trans = reinterpret_cast<uint16_t*>(p->arena + hp.off_trans[k]);
+    p->tables[k].accept = p->arena + hp.off_accept[k];
+  }
+  // a device that cannot give the kernels their shared memory runs the generic path only
+  const bool l_ok = cudaFuncSetAttribute(lines8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kL8DynSmem) == cudaSuccess;
+  if (!l_ok) cudaGetLastError();
+  for (int mode = 0; mode < 3; mode++) {
+    auto place = [&](Lines8Blob& dst, const Lines8Blob& src, size_t off, bool swar) {
+      dst = src;
+      dst.dev = nullptr;
+      dst.ok = false;
+      if (!src.ok || off == kNoImage || !l_ok) return;
+      if (swar && cudaFuncSetAttribute(linesq_kernel_for(src.char_mode), cudaFuncAttributeMaxDynamicSharedMemorySize, kL8DynSmem) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+      }
+      dst.dev = p->arena + off;
+      dst.ok = true;
+    };
+    place(p->l8[mode], hp.l8[mode], hp.off_l8[mode], false);
+    place(p->l16[mode], hp.l16[mode], hp.off_l16[mode], false);
+    place(p->q8[mode], hp.q8[mode], hp.off_q8[mode], true);
+    place(p->q16[mode], hp.q16[mode], hp.off_q16[mode], true);
+  }
+  *out = p;
+  return NDL_OK;
+}
+
+// --- NCCL, bound at run time (libnccl.so.2): only a multi-device pattern needs it, and a host process that already
+// carries an NCCL (PyTorch) must not get a second copy linked in.
+struct NcclApi {
+  typedef struct ncclComm* comm_t;
+  int (*CommInitAll)(comm_t*, int, const int*) = nullptr;
+  int (*CommDestroy)(comm_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+  std::string why;
+  static const NcclApi& get() {
+    static NcclApi api = load();
+    return api;
+  }
+  static NcclApi load() {
+    NcclApi a;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+      a.why = std::string("cannot load libnccl.so.2: ") + dlerror();
+      return a;
+    }
+    a.CommInitAll = reinterpret_cast<decltype(a.CommInitAll)>(dlsym(h, "ncclCommInitAll"));
+    a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    a.Broadcast = reinterpret_cast<decltype(a.Broadcast)>(dlsym(h, "ncclBroadcast"));
+    a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(dlsym(h, "ncclGroupStart"));
+    a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(dlsym(h, "ncclGroupEnd"));
+    a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    a.ok = a.CommInitAll && a.CommDestroy && a.Broadcast && a.GroupStart && a.GroupEnd && a.GetErrorString;
+    if (!a.ok) a.why = "libnccl.so.2 lacks an expected symbol";
+    return a;
+  }
+};
+
+// One NCCL broadcast of the arena from replicas[0] to every other replica (NVLink / NVSwitch), all devices driven by
+// this thread inside one group call.
+static int broadcast_arena(std::vector<ndl_pattern*>& reps) {
+  const NcclApi& nccl = NcclApi::get();
+  if (!nccl.ok) return fail(NDL_ENCCL, nccl.why);
+  const int n = static_cast<int>(reps.size());
+  std::vector<int> devs(n);
+  for (int i = 0; i < n; i++) devs[i] = reps[i]->device;
+  std::vector<NcclApi::comm_t> comms(n, nullptr);
+  int rc = nccl.CommInitAll(comms.data(), n, devs.data());
+  if (rc != 0) return fail(NDL_ENCCL, std::string("ncclCommInitAll failed: ") + nccl.GetErrorString(rc));
+  int result = NDL_OK;
+  std::string msg;
+  rc = nccl.GroupStart();
+  for (int i = 0; i < n && rc == 0; i++) {
+    DeviceGuard guard(devs[i]);
+    rc = nccl.Broadcast(reps[0]->arena, reps[i]->arena, reps[0]->arena_bytes, /*ncclUint8*/ 1, 0, comms[i], nullptr);
+  }
+  const int rc_end = nccl.GroupEnd();
+  if (rc == 0) rc = rc_end;
+  if (rc != 0) {
+    result = NDL_ENCCL;
+    msg = std::string("ncclBroadcast of the table arena failed: ") + nccl.GetErrorString(rc);
+  }
+  for (int i = 0; i < n; i++) {
+    DeviceGuard guard(devs[i]);
+    if (result == NDL_OK && cudaStreamSynchronize(nullptr) != cudaSuccess) {
+      result = NDL_ECUDA;
+      msg = std::string("waiting for the broadcast failed: ") + cudaGetErrorString(cudaGetLastError());
+    }
+  }
+  for (int i = 0; i < n; i++) nccl.CommDestroy(comms[i]);
+  return result == NDL_OK ? NDL_OK : fail(result, msg);
+}
+
+}  // namespace ndl
+
+extern "C" {
+
 int ndl_pattern_create(const uint8_t* blob, size_t blob_len, int device, ndl_pattern** out) {
   if (!out) return fail(NDL_EINVAL, "out must not be NULL");
   *out = nullptr;
-  CompiledPattern cp;
+  HostPattern hp;
   try {
-    cp = deserialize_pattern(blob, blob_len);
+    hp.cp = deserialize_pattern(blob, blob_len);
   } catch (const std::exception& e) {
     return fail(NDL_EBLOB, e.what());
   }
@@ -397,95 +699,206 @@ int ndl_pattern_create(const uint8_t* blob, size_t blob_len, int device, ndl_pat
     cudaGetLastError();
     return fail(NDL_ECUDA, "no CUDA device available (needle_b200 has no CPU fallback)");
   }
-  if (device < 0 || device >= count) return fail(NDL_EINVAL, "device ordinal out of range");
-  NDL_CUDA(cudaSetDevice(device));
-  ndl_pattern* p = new ndl_pattern();
-  p->cp = std::move(cp);
-  p->device = device;
-  cudaDeviceProp prop;
-  cudaError_t e = cudaGetDeviceProperties(&prop, device);
-  if (e != cudaSuccess) {
-    delete p;
-    return fail(NDL_ECUDA, std::string("cudaGetDeviceProperties failed: ") + cudaGetErrorString(e));
-  }
-  p->sm_count = prop.multiProcessorCount;
-  for (int k = 0; k < 4; k++) {
-    p->tables[k].host = build_device_table(p->cp, k);
-    int rc = upload_table(p->tables[k]);
-    if (rc != NDL_OK) {
+  if (device < -1 || device >= count) return fail(NDL_EINVAL, "device ordinal out of range (-1 = every visible device)");
+  build_host_pattern(hp);
+  if (device >= 0 || count == 1) {
+    const int dev = device >= 0 ? device : 0;
+    ndl_pattern* p = nullptr;
+    int rc = instantiate_pattern(hp, dev, &p);
+    if (rc != NDL_OK) return rc;
+    DeviceGuard guard(dev);
+    if (cudaMemcpy(p->arena, hp.arena.host.data(), p->arena_bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+      const std::string why = cudaGetErrorString(cudaGetLastError());
       free_pattern(p);
+      return fail(NDL_ECUDA, "uploading the table arena failed: " + why);
+    }
+    *out = p;
+    return NDL_OK;
+  }
+  // device == -1: one replica per visible GPU.  The arena is uploaded to the first and NCCL-broadcast to the others;
+  // batches are then sharded across the replicas by ndl_match_batch / ndl_match_lines (host buffers).
+  ndl_pattern* root = new ndl_pattern();
+  root->cp = hp.cp;
+  root->device = -1;
+  for (int k = 0; k < 4; k++) root->tables[k].host = hp.tables[k];
+  for (int d = 0; d < count; d++) {
+    ndl_pattern* r = nullptr;
+    int rc = instantiate_pattern(hp, d, &r);
+    if (rc != NDL_OK) {
+      free_pattern(root);
       return rc;
     }
+    root->replicas.push_back(r);
   }
-  // shared-memory images of the byte-input kernel, one per mode
-  cudaError_t ae = cudaFuncSetAttribute(lines8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kL8DynSmem);
-  for (int cw = 1; cw <= 2 && ae == cudaSuccess; cw++)
-    for (int mode = 0; mode < 3; mode++) {
-      const HostDeviceTable& fwd_t = p->tables[mode == NDL_MODE_FIND ? kForwards : mode].host;
-      const bool want_bwd = mode == NDL_MODE_FIND && p->cp.reverse_mode == kReverseTable;
-      std::vector<uint8_t> img;
-      Lines8Blob& b = cw == 1 ? p->l8[mode] : p->l16[mode];
-      const HostDeviceTable* bwd_t = want_bwd ? &p->tables[kBackwards].host : nullptr;
-      // Preference (measured, exp/large_table.py): bank-replicated pair tables, unreplicated pair tables (two dependent
-      // lookups per char cost more than bank conflicts: [Ss]herlock 3.07 against 2.40 TB/s), the stride-1 table in 32
-      // copies, then one plain copy of it (large tables: thousands of states still fit in shared memory).  When find()
-      // needs the table-driven reverse pass, every layout that also holds the BACKWARDS rows comes first: the reverse pass
-      // then runs on the staged tile instead of global memory ((Holmes|Watson|...)+ find: 2.14 against 0.88 TB/s).
-      bool ok = false;
-      if (want_bwd) {
-        ok = lines8_layout(fwd_t, bwd_t, cw, false, img, b);
-        if (!ok) ok = lines8_layout(fwd_t, bwd_t, cw, true, img, b);
-        if (!ok && cw == 1) ok = lines8_layout(fwd_t, bwd_t, cw, true, img, b, true);
-        if (!ok && cw == 1) ok = lines8_layout_s1(fwd_t, bwd_t, 32, img, b);
-        if (!ok && cw == 1) ok = lines8_layout_s1(fwd_t, bwd_t, 1, img, b);
-      }
-      if (!ok) ok = lines8_layout(fwd_t, nullptr, cw, false, img, b);
-      if (!ok) ok = lines8_layout(fwd_t, nullptr, cw, true, img, b);
-      if (!ok && cw == 1) ok = lines8_layout(fwd_t, nullptr, cw, true, img, b, true);
-      if (!ok && cw == 1) ok = lines8_layout_s1(fwd_t, nullptr, 32, img, b);
-      if (!ok && cw == 1) ok = lines8_layout_s1(fwd_t, nullptr, 1, img, b);
-      if (!ok) continue;
-      if (cudaMalloc(&b.dev, img.size()) != cudaSuccess ||
-          cudaMemcpy(b.dev, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
-        cudaGetLastError();
-        free_pattern(p);
-        return fail(NDL_ECUDA, "uploading the shared-memory table image failed");
-      }
-      b.ok = true;
+  {
+    DeviceGuard guard(0);
+    if (cudaMemcpy(root->replicas[0]->arena, hp.arena.host.data(), hp.arena.host.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+      const std::string why = cudaGetErrorString(cudaGetLastError());
+      free_pattern(root);
+      return fail(NDL_ECUDA, "uploading the table arena failed: " + why);
     }
-  // SWAR images (linesq_kernel), where the class map can be evaluated with packed compares
-  for (int cw = 1; cw <= 2 && ae == cudaSuccess; cw++)
-    for (int mode = 0; mode < 3; mode++) {
-      const HostDeviceTable& fwd_t = p->tables[mode == NDL_MODE_FIND ? kForwards : mode].host;
-      const bool want_bwd = mode == NDL_MODE_FIND && p->cp.reverse_mode == kReverseTable;
-      const HostDeviceTable* bwd_t = want_bwd ? &p->tables[kBackwards].host : nullptr;
-      std::vector<uint8_t> img;
-      Lines8Blob b;
-      bool ok = want_bwd && linesq_layout(fwd_t, bwd_t, cw, img, b);
-      if (!ok) ok = linesq_layout(fwd_t, nullptr, cw, img, b);
-      LinesqKernel kern = ok ? linesq_kernel_for(b.char_mode) : nullptr;
-      if (!kern) continue;
-      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kL8DynSmem) != cudaSuccess) {
-        cudaGetLastError();
-        continue;
-      }
-      if (cudaMalloc(&b.dev, img.size()) != cudaSuccess ||
-          cudaMemcpy(b.dev, img.data(), img.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
-        cudaGetLastError();
-        free_pattern(p);
-        return fail(NDL_ECUDA, "uploading the SWAR table image failed");
-      }
-      b.ok = true;
-      (cw == 1 ? p->q8[mode] : p->q16[mode]) = b;
-    }
-  if (ae != cudaSuccess) cudaGetLastError();  // device cannot give the kernel its shared memory: generic path only
-  *out = p;
+  }
+  int rc = broadcast_arena(root->replicas);
+  if (rc != NDL_OK) {
+    free_pattern(root);
+    return rc;
+  }
+  *out = root;
   return NDL_OK;
 }
 
 void ndl_pattern_destroy(ndl_pattern* p) { free_pattern(p); }
 
 }  // extern "C"
+
+// The pipelined NDL_MEM_HOST path of ndl_match_batch / ndl_match_lines on one device; ws_mutex is held.
+static int match_host(ndl_pattern* p, BatchParams bp, int mode, const void* data, const uint64_t* offsets, uint64_t line_chars, uint64_t n,
+                      int char_width, const int32_t* from, uint8_t* matched, int32_t* start, int32_t* end, cudaStream_t stream) {
+  if (offsets && offsets[0] > offsets[n]) return fail(NDL_EINVAL, "offsets must be non-decreasing");
+  const uint64_t base = offsets ? offsets[0] : 0;
+  const uint64_t total_chars = offsets ? offsets[n] - base : n * line_chars;
+  const size_t data_bytes = static_cast<size_t>(total_chars) * char_width;
+  Workspace& ws = p->ws;
+  int rc = ensure_workspace(ws, data_bytes + 64, n, from != nullptr, mode == NDL_MODE_FIND);
+  if (rc != NDL_OK) return rc;
+  if (!p->s_h2d) {
+    NDL_CUDA(cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
+    NDL_CUDA(cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));
+    NDL_CUDA(cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming));
+    for (int k = 0; k < ndl_pattern::kMaxChunks; k++) {
+      NDL_CUDA(cudaEventCreateWithFlags(&p->ev_h2d[k], cudaEventDisableTiming));
+      NDL_CUDA(cudaEventCreateWithFlags(&p->ev_kernel[k], cudaEventDisableTiming));
+    }
+  }
+  // Pageable buffers (a JVM heap array, malloc, numpy) cannot be the end of an asynchronous DMA: their input goes through
+  // the pinned ring, their results through pinned mirrors - the pipeline below stays asynchronous either way.
+  const bool in_pinned = data_bytes == 0 || host_is_pinned(data);
+  const bool off_pinned = !offsets || host_is_pinned(offsets);
+  const bool out_pinned = host_is_pinned(matched) && (mode != NDL_MODE_FIND || (host_is_pinned(start) && host_is_pinned(end)));
+  if (!in_pinned || !off_pinned || (from && !host_is_pinned(from))) {
+    if ((rc = ensure_ring(ws)) != NDL_OK) return rc;
+  }
+  uint8_t* out_m = matched;
+  int32_t *out_s = start, *out_e = end;
+  if (!out_pinned) {
+    if ((rc = ensure_result_mirrors(ws, n, mode == NDL_MODE_FIND)) != NDL_OK) return rc;
+    out_m = ws.h_matched;
+    out_s = ws.h_start;
+    out_e = ws.h_end;
+  }
+  const bool from_pinned = !from || host_is_pinned(from);
+  // the staged copy starts at offsets[0]; bias the data pointer instead of rewriting the offsets
+  bp.data = static_cast<const uint8_t*>(ws.data) - base * char_width;
+  // chunks of about 64 MB of haystack (at most kMaxChunks), cut at line boundaries (host_chunks.h)
+  const int n_chunks = host_chunk_count(data_bytes, n, 64u << 20, ndl_pattern::kMaxChunks);
+  auto off_at = [&](uint64_t i) { return offsets ? offsets[i] : i * line_chars; };
+  auto pipeline = [&]() -> int {
+    NDL_CUDA(cudaEventRecord(p->ev_start, stream));
+    NDL_CUDA(cudaStreamWaitEvent(p->s_h2d, p->ev_start, 0));
+    NDL_CUDA(cudaStreamWaitEvent(p->s_d2h, p->ev_start, 0));
+    uint64_t i0 = 0;
+    for (int k = 0; k < n_chunks && i0 < n; k++) {
+      const uint64_t i1 = host_chunk_end(offsets, n, i0, k, n_chunks);
+      const uint64_t cnt = i1 - i0;
+      const uint64_t o0 = off_at(i0), o1 = off_at(i1);
+      if (o1 < o0 || o1 - base > total_chars) return fail(NDL_EINVAL, "offsets must be non-decreasing");
+      const size_t c0 = static_cast<size_t>(o0 - base) * char_width, c1 = static_cast<size_t>(o1 - base) * char_width;
+      // data first, so that the link is busy while the host looks at this chunk's offsets
+      int r = h2d_copy(ws, static_cast<uint8_t*>(ws.data) + c0, static_cast<const uint8_t*>(data) + base * char_width + c0, c1 - c0, in_pinned,
+                       p->s_h2d);
+      if (r != NDL_OK) return r;
+      // Equally spaced offsets need not cross the link (8 bytes per line: 11 % of the traffic of 64-byte lines): the host
+      // checks every offset of the chunk - exact, one vectorised pass hidden behind the copy above - and the kernel computes
+      // them instead.  The same pass rejects offsets that decrease.
+      OffsetScan sc{true, false, 0};
+      if (offsets) {
+        sc = scan_offsets(offsets + i0, cnt);
+        if (!sc.monotonic) return fail(NDL_EINVAL, "offsets must be non-decreasing");
+        if (!sc.uniform && (r = h2d_copy(ws, ws.offsets + i0, offsets + i0, (cnt + 1) * sizeof(uint64_t), off_pinned, p->s_h2d)) != NDL_OK) return r;
+      }
+      if (from && (r = h2d_copy(ws, ws.from + i0, from + i0, cnt * sizeof(int32_t), from_pinned, p->s_h2d)) != NDL_OK) return r;
+      NDL_CUDA(cudaEventRecord(p->ev_h2d[k], p->s_h2d));
+      NDL_CUDA(cudaStreamWaitEvent(stream, p->ev_h2d[k], 0));
+      BatchParams cb = bp;
+      cb.n = cnt;
+      if (offsets && !sc.uniform) {
+        cb.offsets = ws.offsets + i0;
+      } else {  // line 0 of the chunk is line i0 of the batch
+        cb.offsets = nullptr;
+        cb.line_chars = offsets ? sc.stride : line_chars;
+        cb.data = static_cast<const uint8_t*>(ws.data) + c0;
+      }
+      cb.from = from ? ws.from + i0 : nullptr;
+      cb.matched = ws.matched + i0;
+      cb.start = ws.start + i0;
+      cb.end = ws.end + i0;
+      if ((r = launch_batch(p, cb, char_width, 0, stream)) != NDL_OK) return r;
+      NDL_CUDA(cudaEventRecord(p->ev_kernel[k], stream));
+      NDL_CUDA(cudaStreamWaitEvent(p->s_d2h, p->ev_kernel[k], 0));
+      NDL_CUDA(cudaMemcpyAsync(out_m + i0, ws.matched + i0, cnt, cudaMemcpyDeviceToHost, p->s_d2h));
+      if (mode == NDL_MODE_FIND) {
+        NDL_CUDA(cudaMemcpyAsync(out_s + i0, ws.start + i0, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, p->s_d2h));
+        NDL_CUDA(cudaMemcpyAsync(out_e + i0, ws.end + i0, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, p->s_d2h));
+      }
+      i0 = i1;
+    }
+    return NDL_OK;
+  };
+  rc = pipeline();
+  // whatever happened, nothing of this call may still be in flight when it returns (the caller owns the buffers)
+  const cudaError_t e1 = cudaStreamSynchronize(p->s_h2d), e2 = cudaStreamSynchronize(stream), e3 = cudaStreamSynchronize(p->s_d2h);
+  if (rc != NDL_OK) {
+    cudaGetLastError();
+    return rc;
+  }
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+    return fail(NDL_ECUDA, std::string("host-buffer pipeline failed: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3));
+  if (!out_pinned) {
+    CopyPool& pool = CopyPool::instance();
+    pool.copy(matched, ws.h_matched, n);
+    if (mode == NDL_MODE_FIND) {
+      pool.copy(start, ws.h_start, n * sizeof(int32_t));
+      pool.copy(end, ws.h_end, n * sizeof(int32_t));
+    }
+  }
+  return NDL_OK;
+}
+
+// A multi-device pattern (ndl_pattern_create with device = -1): the batch is cut into one contiguous, byte-balanced range
+// of lines per GPU and every replica runs its own pipelined host path, concurrently.
+static int match_impl(ndl_pattern* p, int mode, const void* data, const uint64_t* offsets, uint64_t line_chars, uint64_t n, int char_width,
+                      const int32_t* from, uint8_t* matched, int32_t* start, int32_t* end, int mem_kind, void* stream_);
+
+static int match_multi(ndl_pattern* p, int mode, const void* data, const uint64_t* offsets, uint64_t line_chars, uint64_t n, int char_width,
+                       const int32_t* from, uint8_t* matched, int32_t* start, int32_t* end, int mem_kind, void* stream_) {
+  if (mem_kind != NDL_MEM_HOST) return fail(NDL_EINVAL, "a multi-device pattern takes host buffers (device memory belongs to one GPU)");
+  if (stream_) return fail(NDL_EINVAL, "a multi-device pattern takes no stream (a stream belongs to one GPU)");
+  if (offsets && offsets[0] > offsets[n]) return fail(NDL_EINVAL, "offsets must be non-decreasing");
+  const int g = static_cast<int>(p->replicas.size());
+  std::vector<uint64_t> bounds(g + 1, n);
+  bounds[0] = 0;
+  for (int k = 0; k + 1 < g; k++) {
+    const uint64_t e = bounds[k] < n ? host_chunk_end(offsets, n, bounds[k], k, g) : n;
+    bounds[k + 1] = e;
+  }
+  std::vector<int> rcs(g, NDL_OK);
+  std::vector<std::string> msgs(g);
+  std::vector<std::thread> threads;
+  auto work = [&](int k) {
+    const uint64_t i0 = bounds[k], cnt = bounds[k + 1] - i0;
+    if (cnt == 0) return;
+    const uint8_t* d = static_cast<const uint8_t*>(data) + (offsets ? 0 : i0 * line_chars * char_width);
+    rcs[k] = match_impl(p->replicas[k], mode, d, offsets ? offsets + i0 : nullptr, line_chars, cnt, char_width, from ? from + i0 : nullptr,
+                        matched + i0, start ? start + i0 : nullptr, end ? end + i0 : nullptr, NDL_MEM_HOST, nullptr);
+    if (rcs[k] != NDL_OK) msgs[k] = ndl_last_error();
+  };
+  for (int k = 1; k < g; k++) threads.emplace_back(work, k);
+  work(0);
+  for (auto& t : threads) t.join();
+  for (int k = 0; k < g; k++)
+    if (rcs[k] != NDL_OK) return fail(rcs[k], "GPU " + std::to_string(p->replicas[k]->device) + ": " + msgs[k]);
+  return NDL_OK;
+}
 
 // ndl_match_batch (offsets != NULL) and ndl_match_lines (offsets == NULL: haystack i = data[i * line_chars ..)).
 static int match_impl(ndl_pattern* p, int mode, const void* data, const uint64_t* offsets, uint64_t line_chars, uint64_t n, int char_width,
@@ -498,8 +911,10 @@ static int match_impl(ndl_pattern* p, int mode, const void* data, const uint64_t
   if (!matched) return fail(NDL_EINVAL, "matched must not be NULL");
   if (mode == NDL_MODE_FIND && (!start || !end)) return fail(NDL_EINVAL, "start and end are required for NDL_MODE_FIND");
   if (!offsets && line_chars >= (1ull << 31)) return fail(NDL_EINVAL, "line_chars must be below 2^31");
+  if (p->device < 0) return match_multi(p, mode, data, offsets, line_chars, n, char_width, from, matched, start, end, mem_kind, stream_);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  NDL_CUDA(cudaSetDevice(p->device));
+  DeviceGuard guard(p->device);
+  NDL_DEVICE(guard);
 
   BatchParams bp;
   std::memset(&bp, 0, sizeof(bp));
@@ -523,100 +938,12 @@ static int match_impl(ndl_pattern* p, int mode, const void* data, const uint64_t
     // total chars are only a sizing hint for the fast path; it reads the real offsets on the device
     return launch_batch(p, bp, char_width, 0, stream);
   }
-
-  // Host buffers: stage in, launch, stage out, all on `stream`, then wait.
-  if (offsets && offsets[0] > offsets[n]) return fail(NDL_EINVAL, "offsets must be non-decreasing");
-  const uint64_t base = offsets ? offsets[0] : 0;
-  const uint64_t total_chars = offsets ? offsets[n] - base : n * line_chars;
-  const size_t data_bytes = static_cast<size_t>(total_chars) * char_width;
   std::lock_guard<std::mutex> lock(p->ws_mutex);
-  Workspace& ws = p->ws;
-  int rc = ensure_workspace(ws, data_bytes + 64, n, from != nullptr, mode == NDL_MODE_FIND);
-  if (rc != NDL_OK) return rc;
-  if (!p->s_h2d) {
-    NDL_CUDA(cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
-    NDL_CUDA(cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));
-    NDL_CUDA(cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming));
-    for (int k = 0; k < ndl_pattern::kMaxChunks; k++) {
-      NDL_CUDA(cudaEventCreateWithFlags(&p->ev_h2d[k], cudaEventDisableTiming));
-      NDL_CUDA(cudaEventCreateWithFlags(&p->ev_kernel[k], cudaEventDisableTiming));
-    }
+  if (!stream) {  // the replicas of a multi-device pattern run concurrently: each on a stream of its own, not the legacy default stream
+    if (!p->s_own) NDL_CUDA(cudaStreamCreateWithFlags(&p->s_own, cudaStreamNonBlocking));
+    stream = p->s_own;
   }
-  // the staged copy starts at offsets[0]; bias the data pointer instead of rewriting the offsets
-  bp.data = static_cast<const uint8_t*>(ws.data) - base * char_width;
-  // chunks of about 64 MB of haystack (at most kMaxChunks), cut at line boundaries
-  int n_chunks = static_cast<int>(data_bytes / (64u << 20)) + 1;
-  if (n_chunks > ndl_pattern::kMaxChunks) n_chunks = ndl_pattern::kMaxChunks;
-  if (static_cast<uint64_t>(n_chunks) > n) n_chunks = static_cast<int>(n);
-  NDL_CUDA(cudaEventRecord(p->ev_start, stream));
-  NDL_CUDA(cudaStreamWaitEvent(p->s_h2d, p->ev_start, 0));
-  NDL_CUDA(cudaStreamWaitEvent(p->s_d2h, p->ev_start, 0));
-  auto off_at = [&](uint64_t i) { return offsets ? offsets[i] : i * line_chars; };
-  uint64_t i0 = 0;
-  for (int k = 0; k < n_chunks; k++) {
-    uint64_t i1 = n;
-    if (k + 1 < n_chunks) {
-      if (offsets) {
-        const uint64_t target = base + total_chars * static_cast<uint64_t>(k + 1) / static_cast<uint64_t>(n_chunks);
-        uint64_t a = i0 + 1, b = n;  // first line index >= i0 + 1 whose offset reaches the target
-        while (a < b) {
-          const uint64_t m = (a + b) / 2;
-          if (offsets[m] < target) a = m + 1; else b = m;
-        }
-        i1 = a;
-      } else {
-        i1 = n * static_cast<uint64_t>(k + 1) / static_cast<uint64_t>(n_chunks);
-        if (i1 <= i0) i1 = i0 + 1;
-      }
-    }
-    const uint64_t cnt = i1 - i0;
-    const size_t c0 = static_cast<size_t>(off_at(i0) - base) * char_width, c1 = static_cast<size_t>(off_at(i1) - base) * char_width;
-    // data first, so that the link is busy while the host looks at this chunk's offsets
-    if (c1 > c0)
-      NDL_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(ws.data) + c0, static_cast<const uint8_t*>(data) + base * char_width + c0, c1 - c0,
-                               cudaMemcpyHostToDevice, p->s_h2d));
-    // Equally spaced offsets need not cross the link (8 bytes per line: 11 % of the traffic of 64-byte lines): the host
-    // checks every offset of the chunk - exact, and hidden behind the copy above - and the kernel computes them instead.
-    bool uniform = false;
-    uint64_t stride = 0;
-    if (offsets) {
-      stride = offsets[i0 + 1] - offsets[i0];
-      uint64_t bad = 0;
-      const uint64_t* o = offsets + i0;
-      for (uint64_t j = 1; j <= cnt; j++) bad |= (o[j] - o[0]) ^ (j * stride);
-      uniform = bad == 0 && stride < (1ull << 31);
-      if (!uniform) NDL_CUDA(cudaMemcpyAsync(ws.offsets + i0, offsets + i0, (cnt + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, p->s_h2d));
-    }
-    if (from) NDL_CUDA(cudaMemcpyAsync(ws.from + i0, from + i0, cnt * sizeof(int32_t), cudaMemcpyHostToDevice, p->s_h2d));
-    NDL_CUDA(cudaEventRecord(p->ev_h2d[k], p->s_h2d));
-    NDL_CUDA(cudaStreamWaitEvent(stream, p->ev_h2d[k], 0));
-    BatchParams cb = bp;
-    cb.n = cnt;
-    if (offsets && !uniform) {
-      cb.offsets = ws.offsets + i0;
-    } else {  // line 0 of the chunk is line i0 of the batch
-      cb.offsets = nullptr;
-      cb.line_chars = offsets ? stride : line_chars;
-      cb.data = static_cast<const uint8_t*>(ws.data) + c0;
-    }
-    cb.from = from ? ws.from + i0 : nullptr;
-    cb.matched = ws.matched + i0;
-    cb.start = ws.start + i0;
-    cb.end = ws.end + i0;
-    rc = launch_batch(p, cb, char_width, 0, stream);
-    if (rc != NDL_OK) return rc;
-    NDL_CUDA(cudaEventRecord(p->ev_kernel[k], stream));
-    NDL_CUDA(cudaStreamWaitEvent(p->s_d2h, p->ev_kernel[k], 0));
-    NDL_CUDA(cudaMemcpyAsync(matched + i0, ws.matched + i0, cnt, cudaMemcpyDeviceToHost, p->s_d2h));
-    if (mode == NDL_MODE_FIND) {
-      NDL_CUDA(cudaMemcpyAsync(start + i0, ws.start + i0, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, p->s_d2h));
-      NDL_CUDA(cudaMemcpyAsync(end + i0, ws.end + i0, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, p->s_d2h));
-    }
-    i0 = i1;
-  }
-  NDL_CUDA(cudaStreamSynchronize(p->s_d2h));
-  NDL_CUDA(cudaStreamSynchronize(stream));
-  return NDL_OK;
+  return match_host(p, bp, mode, data, offsets, line_chars, n, char_width, from, matched, start, end, stream);
 }
 
 extern "C" {
@@ -632,6 +959,23 @@ int ndl_match_lines(ndl_pattern* p, int mode, const void* data, uint64_t n, uint
   return match_impl(p, mode, data, nullptr, line_chars, n, char_width, nullptr, matched, start, end, mem_kind, stream);
 }
 
+// Page-locked host memory for the caller's batch buffers (a JNI shim backs a direct ByteBuffer with it): buffers from here
+// are DMA'd directly, anything else goes through the library's bounce ring.
+void* ndl_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    fail(NDL_ENOMEM, std::string("cudaHostAlloc failed: ") + cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  return p;
+}
+
+void ndl_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int ndl_pattern_device_count(const ndl_pattern* p) { return !p ? 0 : p->device < 0 ? static_cast<int>(p->replicas.size()) : 1; }
+
 int ndl_find_all_batch(ndl_pattern* p, const void* data, const uint64_t* offsets, uint64_t n, int char_width, uint32_t* counts,
                        const uint64_t* match_offsets, int32_t* starts, int32_t* ends, int mem_kind, void* stream_) {
   if (!p) return fail(NDL_EINVAL, "pattern must not be NULL");
@@ -640,8 +984,10 @@ int ndl_find_all_batch(ndl_pattern* p, const void* data, const uint64_t* offsets
   if (n == 0) return NDL_OK;
   if (!offsets || !counts) return fail(NDL_EINVAL, "offsets and counts must not be NULL");
   if (match_offsets && (!starts || !ends)) return fail(NDL_EINVAL, "starts and ends are required with match_offsets");
+  if (p->device < 0) return fail(NDL_EINVAL, "ndl_find_all_batch needs a single-device pattern");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  NDL_CUDA(cudaSetDevice(p->device));
+  DeviceGuard guard(p->device);
+  NDL_DEVICE(guard);
   FindAllParams q;
   std::memset(&q, 0, sizeof(q));
   q.b.n = n;
@@ -674,7 +1020,9 @@ int ndl_find_all_batch(ndl_pattern* p, const void* data, const uint64_t* offsets
     return launch();
   }
   // host buffers: stage in, launch, stage out on `stream`, then wait
-  if (offsets[0] > offsets[n]) return fail(NDL_EINVAL, "offsets must be non-decreasing");
+  if (offsets[0] > offsets[n] || !scan_offsets(offsets, n).monotonic) return fail(NDL_EINVAL, "offsets must be non-decreasing");
+  if (match_offsets && (match_offsets[0] > match_offsets[n] || !scan_offsets(match_offsets, n).monotonic))
+    return fail(NDL_EINVAL, "match_offsets must be non-decreasing");
   const uint64_t base = offsets[0];
   const size_t data_bytes = static_cast<size_t>(offsets[n] - base) * char_width;
   const uint64_t total = match_offsets ? match_offsets[n] - match_offsets[0] : 0;
@@ -682,21 +1030,32 @@ int ndl_find_all_batch(ndl_pattern* p, const void* data, const uint64_t* offsets
   Workspace& ws = p->ws;
   int rc = ensure_workspace(ws, data_bytes + 64, n, false, true);
   if (rc != NDL_OK) return rc;
-  uint32_t* d_counts = nullptr;
-  uint64_t* d_moff = nullptr;
-  int32_t *d_starts = nullptr, *d_ends = nullptr;
-  struct Guard { void *a, *b, *c, *d; ~Guard() { cudaFree(a); cudaFree(b); cudaFree(c); cudaFree(d); } } guard{nullptr, nullptr, nullptr, nullptr};
-  NDL_CUDA(cudaMalloc(&d_counts, n * sizeof(uint32_t)));
-  guard.a = d_counts;
-  if (match_offsets) {
-    NDL_CUDA(cudaMalloc(&d_moff, (n + 1) * sizeof(uint64_t)));
-    guard.b = d_moff;
-    NDL_CUDA(cudaMalloc(&d_starts, (total + 1) * sizeof(int32_t)));
-    guard.c = d_starts;
-    NDL_CUDA(cudaMalloc(&d_ends, (total + 1) * sizeof(int32_t)));
-    guard.d = d_ends;
-    NDL_CUDA(cudaMemcpyAsync(d_moff, match_offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
+  // grow-only staging of the counts / CSR arrays (no allocation on the steady-state path)
+  if (n + 1 > ws.counts_cap) {
+    cudaFree(ws.counts);
+    cudaFree(ws.match_offsets);
+    ws.counts = nullptr;
+    ws.match_offsets = nullptr;
+    ws.counts_cap = 0;
+    const size_t cap = n + n / 8 + 16;
+    NDL_CUDA(cudaMalloc(&ws.counts, cap * sizeof(uint32_t)));
+    NDL_CUDA(cudaMalloc(&ws.match_offsets, (cap + 1) * sizeof(uint64_t)));
+    ws.counts_cap = cap;
   }
+  if (match_offsets && total + 1 > ws.all_cap) {
+    cudaFree(ws.all_starts);
+    cudaFree(ws.all_ends);
+    ws.all_starts = ws.all_ends = nullptr;
+    ws.all_cap = 0;
+    const size_t cap = total + total / 8 + 16;
+    NDL_CUDA(cudaMalloc(&ws.all_starts, cap * sizeof(int32_t)));
+    NDL_CUDA(cudaMalloc(&ws.all_ends, cap * sizeof(int32_t)));
+    ws.all_cap = cap;
+  }
+  uint32_t* d_counts = ws.counts;
+  uint64_t* d_moff = match_offsets ? ws.match_offsets : nullptr;
+  int32_t *d_starts = match_offsets ? ws.all_starts : nullptr, *d_ends = match_offsets ? ws.all_ends : nullptr;
+  if (match_offsets) NDL_CUDA(cudaMemcpyAsync(d_moff, match_offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
   NDL_CUDA(cudaMemcpyAsync(ws.offsets, offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, stream));
   if (data_bytes)
     NDL_CUDA(cudaMemcpyAsync(ws.data, static_cast<const uint8_t*>(data) + base * char_width, data_bytes, cudaMemcpyHostToDevice, stream));
@@ -718,6 +1077,9 @@ int ndl_find_all_batch(ndl_pattern* p, const void* data, const uint64_t* offsets
 }
 }  // extern "C"
 
+// device scratch of the ndl_find_long family (kept with the pattern; calls are serialised by ws_mutex)
+struct LongScratch { SeqResult r; unsigned long long first_seg, first_bad; int64_t back; Long8Epilogue epi; int64_t back2[2]; };
+
 static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, int char_width, int64_t from, int32_t entry_state,
                           int64_t last_init, uint8_t* matched, int64_t* start, int64_t* end, int32_t* exit_state, int mem_kind,
                           void* stream_) {
@@ -726,8 +1088,10 @@ static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, in
   if (mem_kind != NDL_MEM_HOST && mem_kind != NDL_MEM_DEVICE) return fail(NDL_EINVAL, "mem_kind must be NDL_MEM_HOST or NDL_MEM_DEVICE");
   if (!matched || !end || (!start && !exit_state)) return fail(NDL_EINVAL, "matched, start and end must not be NULL");
   if (from < 0) return fail(NDL_EINVAL, "from must be >= 0");
+  if (p->device < 0) return fail(NDL_EINVAL, "ndl_find_long needs a single-device pattern");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  NDL_CUDA(cudaSetDevice(p->device));
+  DeviceGuard guard(p->device);
+  NDL_DEVICE(guard);
   const int64_t n = static_cast<int64_t>(n_chars);
   const int64_t kIntMax = INT64_MAX;
 
@@ -741,8 +1105,8 @@ static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, in
     d_data = static_cast<const uint8_t*>(p->ws.data);
   }
   // scratch: SeqResult + 2 atomics + back result (kept with the pattern; calls are serialised by ws_mutex)
-  struct Scratch { SeqResult r; unsigned long long first_seg, first_bad; int64_t back; Long8Epilogue epi; };
-  if (!p->ws.long_scratch) NDL_CUDA(cudaMalloc(&p->ws.long_scratch, sizeof(Scratch)));
+  if (!p->ws.long_scratch) NDL_CUDA(cudaMalloc(&p->ws.long_scratch, sizeof(LongScratch)));
+  typedef LongScratch Scratch;
   Scratch* d_sc = static_cast<Scratch*>(p->ws.long_scratch);
   Scratch h;
   const DevTable fwd = p->tables[kForwards].view();
@@ -962,8 +1326,10 @@ int ndl_find_long_back(ndl_pattern* p, const void* data, uint64_t n_chars, int c
   const int dead = p->tables[kBackwards].host.n_states;
   if (entry_state < 0 || entry_state > dead) return fail(NDL_EINVAL, "entry_state out of range");
   if (lower < 0 || index >= static_cast<int64_t>(n_chars)) return fail(NDL_EINVAL, "index / lower out of range");
+  if (p->device < 0) return fail(NDL_EINVAL, "ndl_find_long_back needs a single-device pattern");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  NDL_CUDA(cudaSetDevice(p->device));
+  DeviceGuard guard(p->device);
+  NDL_DEVICE(guard);
   std::lock_guard<std::mutex> lock(p->ws_mutex);
   const uint8_t* d_data = static_cast<const uint8_t*>(data);
   if (mem_kind == NDL_MEM_HOST && index >= lower) {
@@ -974,9 +1340,8 @@ int ndl_find_long_back(ndl_pattern* p, const void* data, uint64_t n_chars, int c
     NDL_CUDA(cudaMemcpyAsync(p->ws.data, static_cast<const uint8_t*>(data) + w0, w1 - w0, cudaMemcpyHostToDevice, stream));
     d_data = static_cast<const uint8_t*>(p->ws.data) - w0;
   }
-  int64_t* d_out = nullptr;
-  NDL_CUDA(cudaMalloc(&d_out, 2 * sizeof(int64_t)));
-  struct Guard { void* a; ~Guard() { cudaFree(a); } } guard{d_out};
+  if (!p->ws.long_scratch) NDL_CUDA(cudaMalloc(&p->ws.long_scratch, sizeof(LongScratch)));
+  int64_t* d_out = static_cast<LongScratch*>(p->ws.long_scratch)->back2;
   BatchParams bp;
   std::memset(&bp, 0, sizeof(bp));
   bp.reverse_mode = p->cp.reverse_mode;

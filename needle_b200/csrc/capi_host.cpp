@@ -6,6 +6,7 @@
 #include "capi_internal.h"
 #include "host/ast.h"
 #include "host/pattern.h"
+#include "host_chunks.h"
 #include "needle_b200.h"
 
 namespace ndl {
@@ -119,7 +120,7 @@ int ndl_blob_info_get(const uint8_t* blob, size_t blob_len, ndl_blob_info* out) 
 
 const char* ndl_last_error(void) { return g_last_error.c_str(); }
 
-const char* ndl_version(void) { return "needle_b200 0.1.0 (blob v1, sm_100a)"; }
+const char* ndl_version(void) { return "needle_b200 0.2.0 (blob v2, sm_100a)"; }
 
 }  // extern "C"
 
@@ -156,4 +157,26 @@ extern "C" int ndl_debug_dfa(const uint16_t* regex_utf16, size_t n_chars, int fl
   } catch (const std::exception& e) {
     return fail(NDL_ECOMPILE, e.what());
   }
+}
+
+// Test hook (not part of include/needle_b200.h; host only): how the NDL_MEM_HOST path of ndl_match_batch would cut a batch
+// into pipeline chunks (host_chunks.h - the same functions capi_device.cu calls).  bounds receives the chunk boundaries
+// (bounds[0] = 0, bounds[k + 1] = end of chunk k; room for max_chunks + 1 entries), flags per chunk bit 0 = offsets equally
+// spaced, bit 1 = offsets non-decreasing.  Returns the number of chunks.
+extern "C" int ndl_debug_plan_chunks(const uint64_t* offsets, uint64_t line_chars, uint64_t n, int char_width, uint64_t chunk_bytes,
+                                     int max_chunks, uint64_t* bounds, int32_t* flags) {
+  const uint64_t total = offsets ? offsets[n] - offsets[0] : n * line_chars;
+  const int n_chunks = host_chunk_count(static_cast<size_t>(total) * char_width, n, chunk_bytes, max_chunks);
+  int used = 0;
+  uint64_t i0 = 0;
+  bounds[0] = 0;
+  for (int k = 0; k < n_chunks && i0 < n; k++) {
+    const uint64_t i1 = host_chunk_end(offsets, n, i0, k, n_chunks);
+    OffsetScan sc{true, true, line_chars};
+    if (offsets) sc = scan_offsets(offsets + i0, i1 - i0);
+    flags[used] = (sc.uniform ? 1 : 0) | (sc.monotonic ? 2 : 0);
+    bounds[++used] = i1;
+    i0 = i1;
+  }
+  return used;
 }

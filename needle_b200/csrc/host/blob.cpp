@@ -9,6 +9,9 @@
 //   u32 n_runs | n_runs x { u16 last_char, u16 class }      -- BYTE_CLASSES as runs (DFAClassBuilder.java:280-299)
 //   4 x { i32 n_states | i32 width | i32 max_char | u8 accepting[n_states] (padded to 4) |
 //         i16 entries[n_states * stride] (padded to 4) }    -- MATCHES, CONTAINEDIN, FORWARDS, BACKWARDS
+//   version >= 2: the accelerator record (pattern.h Accel; DFAClassBuilder.java:365-429)
+//     u32 "ACCL" | u32 flag bits | i32 post_prefix_state | i32 follow_state | i32 pred_kind | i32 pred_a | i32 pred_b |
+//     3 x { u32 n | u16 chars[n] (padded to 4) }  -- PREFIX, SUFFIX, INFIX | u8 first_byte_mask[129] (padded to 4)
 //   u32 fnv1a of everything before it
 #include <cstring>
 #include <stdexcept>
@@ -62,6 +65,8 @@ struct Reader {
   }
 };
 
+constexpr uint32_t kAccelMagic = 0x4C434341u;  // "ACCL"
+
 uint32_t fnv1a(const uint8_t* p, size_t n) {
   uint32_t h = 2166136261u;
   for (size_t i = 0; i < n; i++) {
@@ -103,6 +108,24 @@ std::vector<uint8_t> serialize_pattern(const CompiledPattern& p) {
     for (int16_t e : t.entries) w.u16(static_cast<uint16_t>(e));
     w.pad4();
   }
+  const Accel& a = p.accel;
+  w.u32(kAccelMagic);
+  w.u32((a.use_prefix ? 1u : 0) | (a.use_suffix ? 2u : 0) | (a.use_infixes ? 4u : 0) | (a.use_max_start ? 8u : 0) |
+        (a.can_seek_for_predicate ? 16u : 0) | (a.has_first_byte_mask ? 32u : 0) | (a.byte_check_first_char ? 64u : 0) |
+        (a.post_prefix_accepting ? 128u : 0) | (a.follow_accepting ? 256u : 0) | (a.inner_must_call_was_accepted ? 512u : 0) |
+        (a.present ? 1024u : 0));
+  w.i32(a.post_prefix_state);
+  w.i32(a.follow_state);
+  w.i32(a.pred_kind);
+  w.i32(a.pred_a);
+  w.i32(a.pred_b);
+  for (const std::u16string* str : {&a.prefix, &a.suffix, &a.infix}) {
+    w.u32(static_cast<uint32_t>(str->size()));
+    for (char16_t c : *str) w.u16(static_cast<uint16_t>(c));
+    w.pad4();
+  }
+  for (int i = 0; i < 129; i++) w.buf.push_back(a.first_byte_mask[i]);
+  w.pad4();
   w.u32(fnv1a(w.buf.data(), w.buf.size()));
   return w.buf;
 }
@@ -112,7 +135,7 @@ CompiledPattern deserialize_pattern(const uint8_t* blob, size_t len) {
   Reader r{blob, len};
   if (r.u32() != kBlobMagic) throw std::runtime_error("not a needle_b200 pattern blob (bad magic)");
   int32_t version = r.i32();
-  if (version != kBlobVersion) throw std::runtime_error("unsupported pattern blob version " + std::to_string(version));
+  if (version != 1 && version != kBlobVersion) throw std::runtime_error("unsupported pattern blob version " + std::to_string(version));
   uint32_t stored = 0;
   std::memcpy(&stored, blob + len - 4, 4);  // little-endian hosts only (x86-64 / aarch64)
   if (fnv1a(blob, len - 4) != stored) throw std::runtime_error("pattern blob checksum mismatch");
@@ -155,6 +178,35 @@ CompiledPattern deserialize_pattern(const uint8_t* blob, size_t len) {
       if (e < -1 || e >= t.n_states) throw std::runtime_error("pattern blob transition out of range");
       t.entries[i] = e;
     }
+    r.pad4();
+  }
+  if (version >= 2) {
+    if (r.u32() != kAccelMagic) throw std::runtime_error("pattern blob accelerator record missing");
+    Accel& a = p.accel;
+    const uint32_t f = r.u32();
+    a.use_prefix = f & 1; a.use_suffix = f & 2; a.use_infixes = f & 4; a.use_max_start = f & 8;
+    a.can_seek_for_predicate = f & 16; a.has_first_byte_mask = f & 32; a.byte_check_first_char = f & 64;
+    a.post_prefix_accepting = f & 128; a.follow_accepting = f & 256; a.inner_must_call_was_accepted = f & 512;
+    a.present = f & 1024;
+    a.post_prefix_state = r.i32();
+    a.follow_state = r.i32();
+    a.pred_kind = r.i32();
+    a.pred_a = r.i32();
+    a.pred_b = r.i32();
+    const int n_fwd = p.tables[kForwards].n_states;
+    if (a.post_prefix_state < 0 || a.post_prefix_state >= n_fwd || a.follow_state < 0 || a.follow_state >= n_fwd || a.pred_kind < 0 ||
+        a.pred_kind > 3)
+      throw std::runtime_error("pattern blob accelerator record out of range");
+    for (std::u16string* str : {&a.prefix, &a.suffix, &a.infix}) {
+      const uint32_t n = r.u32();
+      if (n > 65536) throw std::runtime_error("pattern blob accelerator string too long");
+      str->clear();
+      for (uint32_t i = 0; i < n; i++) str->push_back(static_cast<char16_t>(r.u16()));
+      r.pad4();
+    }
+    r.need(129);
+    for (int i = 0; i < 129; i++) a.first_byte_mask[i] = blob[r.pos + i];
+    r.pos += 129;
     r.pad4();
   }
   if (r.pos + 4 != len) throw std::runtime_error("pattern blob has trailing bytes");

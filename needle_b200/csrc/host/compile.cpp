@@ -7,6 +7,7 @@
 
 #include "ast.h"
 #include "automata.h"
+#include "factorization.h"
 #include "needle_b200.h"
 #include "pattern.h"
 
@@ -104,9 +105,11 @@ CompiledPattern compile_pattern(const std::u16string& regex, int flags) {
     Node* node = parse_regex(ast, regex, flags);
     CompiledPattern p;
     p.flags = flags;
-    // Factorization.buildFactorization (Factorization.java:101-106): only min/max length reach the results
-    p.min_length = Ast::min_length(node);
-    p.max_length = Ast::max_length(node);
+    // Factorization.buildFactorization (Factorization.java:101-106): only min/max length reach the results; the literal
+    // factors feed the search accelerators (p.accel, below)
+    const Factorization factorization = build_factorization(node);
+    p.min_length = factorization.min_length;
+    p.max_length = factorization.max_length;
 
     const bool lml = (flags & NDL_LEFTMOST_LONGEST) == NDL_LEFTMOST_LONGEST;
     std::vector<Instr> forward = build_program(node, lml);
@@ -139,6 +142,8 @@ CompiledPattern compile_pattern(const std::u16string& regex, int flags) {
       p.class_map = ubc.wide;
       for (int k = 0; k < 4; k++) p.tables[k] = exact_table(*all[k], ubc, p.stride);
     }
+
+    p.accel = build_accel(factorization, *search);
 
     // How find() derives start() from end() (DFAClassBuilder.java:119-121, 588-614, 640-657)
     if (p.max_length != kNoMax && p.min_length == p.max_length) {

@@ -40,6 +40,11 @@ def lib():
         L.ndlo_backwards_state_count.argtypes = [vp]
         L.ndlo_backwards_root_accepting.argtypes = [vp]
         L.ndlo_match_batch.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_uint64, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int]
+        L.ndlo_match_batch_accel.argtypes = L.ndlo_match_batch.argtypes
+        L.ndlo_index_forwards_accel.argtypes = [vp, vp, i64, ctypes.c_int, i64]
+        L.ndlo_index_forwards_accel.restype = i64
+        L.ndlo_accel_summary.argtypes = [vp]
+        L.ndlo_accel_summary.restype = ctypes.c_char_p
         _lib = L
     return _lib
 
@@ -174,8 +179,19 @@ class Oracle:
     def backwards_root_accepting(self):
         return bool(lib().ndlo_backwards_root_accepting(self._h))
 
+    def accel_summary(self) -> str:
+        """Which accelerators the accelerated indexForwards of this pattern uses (CompilationPolicy restated)."""
+        return lib().ndlo_accel_summary(self._h).decode()
+
+    def index_forwards(self, s, from_=0, accelerated=False):
+        buf, n, cw = _encode(s)
+        fn = lib().ndlo_index_forwards_accel if accelerated else lib().ndlo_index_forwards
+        return fn(self._h, buf, n, cw, from_)
+
     # -- batches
-    def match_batch(self, mode, data, offsets, char_width=1, from_=None, threads=1):
+    def match_batch(self, mode, data, offsets, char_width=1, from_=None, threads=1, accelerated=False):
+        """ndlo_match_batch.  accelerated: find() runs indexForwards with the accelerators the reference's CompilationPolicy picks
+        (indexOf prefix / suffix / infix seek, predicate seek, first-byte mask) - same results, the speed the JVM version has."""
         n = len(offsets) - 1
         data = np.ascontiguousarray(data).view(np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
@@ -185,10 +201,11 @@ class Oracle:
         if from_ is not None:
             from_ = np.ascontiguousarray(from_, dtype=np.int32)
         if n:
-            rc = lib().ndlo_match_batch(self._h, mode, data.ctypes.data if data.size else None, offsets.ctypes.data, n, char_width,
-                                        from_.ctypes.data if from_ is not None else None, matched.ctypes.data,
-                                        start.ctypes.data if start is not None else None,
-                                        end.ctypes.data if end is not None else None, threads)
+            fn = lib().ndlo_match_batch_accel if accelerated else lib().ndlo_match_batch
+            rc = fn(self._h, mode, data.ctypes.data if data.size else None, offsets.ctypes.data, n, char_width,
+                    from_.ctypes.data if from_ is not None else None, matched.ctypes.data,
+                    start.ctypes.data if start is not None else None,
+                    end.ctypes.data if end is not None else None, threads)
             if rc != 0:
                 raise RuntimeError("ndlo_match_batch failed")
         return matched, start, end

@@ -15,6 +15,9 @@ def test_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["metric"] == "input_gb_per_s_scanned" and line["unit"] == "GB/s"
     assert line["higher_is_better"] is True and line["steps"] == 2 and line["warmup"] == 1 and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    # the timed loop carries the reference's search accelerators; the plain loops are reported beside it
+    assert line["cpu_baseline"]["variant"] == "port+accelerators" and line["cpu_baseline"]["plain_value"] > 0
+    assert "indexOf(PREFIX)" in line["cpu_baseline"]["accelerators"]
     assert line["e2e"] == {"value": line["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and line["gpu_launches"] == 0
 
