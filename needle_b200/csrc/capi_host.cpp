@@ -180,3 +180,31 @@ extern "C" int ndl_debug_plan_chunks(const uint64_t* offsets, uint64_t line_char
   }
   return used;
 }
+
+// Test hook (not part of include/needle_b200.h): the byte classes EACH of the four automata of a pattern would have on
+// its own (DFA.byteClasses applied to it), in table order MATCHES, CONTAINEDIN, FORWARDS, BACKWARDS; out = 4 x 65536 ids.
+// The reference derives ONE class map, from the search automaton only, and shares it between all four tables
+// (DFAClassBuilder.java:67-76, with the TODO "test whether it matters that the four DFAs can have different
+// byteClasses"): where another automaton distinguishes chars that the search automaton does not, that automaton's
+// table is coarser than the automaton.  The generative differential test uses this to tell such patterns.
+extern "C" int ndl_debug_class_maps(const uint16_t* regex_utf16, size_t n_chars, int flags, uint16_t* out) {
+  try {
+    std::u16string regex(reinterpret_cast<const char16_t*>(regex_utf16), n_chars);
+    Ast ast;
+    Node* node = parse_regex(ast, regex, flags);
+    const bool lml = (flags & NDL_LEFTMOST_LONGEST) == NDL_LEFTMOST_LONGEST;
+    std::vector<Instr> forward = build_program(node, lml);
+    std::vector<Instr> reversed = build_program(ast.reversed(node), lml);
+    std::unique_ptr<Dfa> dfas[4] = {compile_dfa(forward, ConversionMode::Basic), compile_dfa(forward, ConversionMode::ContainedIn),
+                                    compile_dfa(forward, ConversionMode::DfaSearch), compile_dfa(reversed, ConversionMode::Basic)};
+    for (int k = 0; k < 4; k++) {
+      ByteClasses bc = byte_classes(*dfas[k]);
+      for (int c = 0; c < 65536; c++) out[k * 65536 + c] = bc.wide[c];
+    }
+    return NDL_OK;
+  } catch (const SyntaxError& e) {
+    return fail(NDL_ESYNTAX, e.what());
+  } catch (const std::exception& e) {
+    return fail(NDL_ECOMPILE, e.what());
+  }
+}
