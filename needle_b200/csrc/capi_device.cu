@@ -308,24 +308,22 @@ static int launch_batch(ndl_pattern* p, const BatchParams& bp, int char_width, u
   if (bp.n == 0) return NDL_OK;
   (void)total_chars;
   const Lines8Blob& qimg = char_width == 1 ? p->q8[bp.mode] : p->q16[bp.mode];
-  if (qimg.ok && bp.n >= 2 && bp.n < (1ull << 31)) {
-    Lines8Params lp;
-    fill_lines8_params(lp, bp, qimg);
-    const uint64_t per_cta = 32ull * 21;  // lines a CTA's warps take per round
-    const uint64_t want = (bp.n + per_cta - 1) / per_cta;
-    const int blocks = static_cast<int>(want < static_cast<uint64_t>(p->sm_count) ? want : p->sm_count);
-    linesq_kernel_for(qimg.char_mode)<<<blocks, kQThreads, kL8DynSmem, stream>>>(lp);
-    g_launches.fetch_add(1);
-    NDL_CUDA(cudaGetLastError());
-    return NDL_OK;
-  }
-  const Lines8Blob& img = char_width == 1 ? p->l8[bp.mode] : p->l16[bp.mode];
-  if (img.ok && bp.n >= 2 && bp.n < (1ull << 31)) {
+  const Lines8Blob& limg = char_width == 1 ? p->l8[bp.mode] : p->l16[bp.mode];
+  const bool tiles = (qimg.ok || limg.ok) && bp.n >= 2 && bp.n < (1ull << 31);
+  if (tiles) {
+    const Lines8Blob& img = qimg.ok ? qimg : limg;
     Lines8Params lp;
     fill_lines8_params(lp, bp, img);
-    uint64_t max_tiles = (bp.n + 1023) / 1024;  // a CTA's 32 warps take 32 lines each per round
-    int blocks = static_cast<int>(max_tiles < static_cast<uint64_t>(p->sm_count) ? max_tiles : p->sm_count);
-    lines8_kernel<<<blocks, kL8Threads, kL8DynSmem, stream>>>(lp);
+    if (qimg.ok) {
+      const uint64_t per_cta = 32ull * 21;  // lines a CTA's warps take per round
+      const uint64_t want = (bp.n + per_cta - 1) / per_cta;
+      const int blocks = static_cast<int>(want < static_cast<uint64_t>(p->sm_count) ? want : p->sm_count);
+      linesq_kernel_for(qimg.char_mode)<<<blocks, kQThreads, kL8DynSmem, stream>>>(lp);
+    } else {
+      uint64_t max_tiles = (bp.n + 1023) / 1024;  // a CTA's 32 warps take 32 lines each per round
+      int blocks = static_cast<int>(max_tiles < static_cast<uint64_t>(p->sm_count) ? max_tiles : p->sm_count);
+      lines8_kernel<<<blocks, kL8Threads, kL8DynSmem, stream>>>(lp);
+    }
     g_launches.fetch_add(1);
     NDL_CUDA(cudaGetLastError());
     return NDL_OK;

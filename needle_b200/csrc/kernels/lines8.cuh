@@ -134,6 +134,7 @@ struct SwarDev {
   uint32_t copy_bytes;    // bytes of one copy inside a 128-byte line (4 * 32 / R)
 };
 
+
 // Device image for one (mode, char width): [cmap 64 KB][trans], plus what the kernel needs to start a walk.
 struct Lines8Blob {
   uint8_t* dev = nullptr;
@@ -1032,6 +1033,7 @@ __device__ __forceinline__ void l8_run_ragged(const Lines8Params& p, const L8Ctx
     c = cb + pb.count;
   }
 }
+
 
 template <int CM>
 __device__ __forceinline__ void l8_dispatch(const Lines8Params& p, const L8Ctx& cx, int log2cpl, uint32_t buf0, uint32_t buf1,
