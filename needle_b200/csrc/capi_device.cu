@@ -997,6 +997,26 @@ int ndl_find_all_batch(ndl_pattern* p, const void* data, const uint64_t* offsets
   q.b.fwd = p->tables[kForwards].view();
   q.b.bwd = p->tables[kBackwards].view();
   auto launch = [&]() -> int {
+    // the tile kernels (staged lines, shared-memory tables) when the pattern has an image for find(); mode kModeFindAll
+    const Lines8Blob& qimg = char_width == 1 ? p->q8[NDL_MODE_FIND] : p->q16[NDL_MODE_FIND];
+    const Lines8Blob& limg = char_width == 1 ? p->l8[NDL_MODE_FIND] : p->l16[NDL_MODE_FIND];
+    if ((qimg.ok || limg.ok) && n >= 2 && n < (1ull << 31)) {
+      BatchParams bp = q.b;
+      bp.mode = kModeFindAll;
+      bp.counts = q.counts;
+      bp.match_offsets = q.match_offsets;
+      bp.start = q.starts;
+      bp.end = q.ends;
+      Lines8Params lp;
+      fill_lines8_params(lp, bp, qimg.ok ? qimg : limg);
+      const uint64_t want_ctas = (n + 671) / 672;
+      const int blocks = static_cast<int>(want_ctas < static_cast<uint64_t>(p->sm_count) ? want_ctas : p->sm_count);
+      if (qimg.ok) linesq_kernel_for(qimg.char_mode)<<<blocks, kQThreads, kL8DynSmem, stream>>>(lp);
+      else lines8_kernel<<<blocks, kL8Threads, kL8DynSmem, stream>>>(lp);
+      g_launches.fetch_add(1);
+      NDL_CUDA(cudaGetLastError());
+      return NDL_OK;
+    }
     const int threads = 256;
     const uint64_t want = (n + threads - 1) / threads, max_blocks = static_cast<uint64_t>(p->sm_count) * 32;
     const int blocks = static_cast<int>(want < max_blocks ? want : max_blocks);

@@ -30,7 +30,12 @@ struct BatchParams {
   int reverse_mode, reverse_char;
   DevTable fwd;  // the table the mode walks forwards: MATCHES / CONTAINEDIN / FORWARDS
   DevTable bwd;  // BACKWARDS (find only)
+  // mode kModeFindAll (ndl_find_all_batch on the tile kernels): counts[n]; with match_offsets, match k of haystack i is
+  // stored in start / end at match_offsets[i] + k while that is below match_offsets[i + 1]
+  uint32_t* counts;
+  const uint64_t* match_offsets;
 };
+constexpr int kModeFindAll = 3;  // internal: iterated find() (`while (m.find())`), forward table = FORWARDS
 
 // offset (in chars) of haystack i: from the offsets array, or computed for fixed-length lines - which saves the
 // 8 bytes per line of HBM traffic (and of PCIe traffic on the host path) that reading them would cost
@@ -131,6 +136,34 @@ __global__ void __launch_bounds__(256) generic_batch_kernel(const BatchParams p)
 // reference: here it is reported once and ends the loop, so `from` strictly increases and the loop terminates.
 // counts[i] = number of matches; when match_offsets != NULL, match k of haystack i is stored at
 // match_offsets[i] + k as long as that is below match_offsets[i + 1] (two-pass CSR: count, scan, fill).
+// The loop for one haystack, straight from global memory.
+template <typename CharT>
+__device__ __forceinline__ void dev_find_all_line(const BatchParams& p, uint64_t i) {
+  const uint64_t o0 = batch_off(p, i), o1 = batch_off(p, i + 1);
+  const CharT* s = static_cast<const CharT*>(p.data) + o0;
+  const int64_t len = static_cast<int64_t>(o1 - o0);
+  uint64_t out = 0, cap = 0;
+  if (p.match_offsets) {
+    out = p.match_offsets[i];
+    cap = p.match_offsets[i + 1] - out;
+  }
+  uint32_t count = 0;
+  int64_t from = 0;
+  for (;;) {
+    const int64_t e = dev_index_forwards<CharT>(p, s, len, from);
+    if (e == -1) break;
+    const int64_t st = (p.reverse_mode == 2) ? e - p.min_length : dev_index_backwards<CharT>(p, s, e - 1, from, 0x7fffffff);
+    if (count < cap) {
+      p.start[out + count] = static_cast<int32_t>(st);
+      p.end[out + count] = static_cast<int32_t>(e);
+    }
+    count++;
+    if (e <= from) break;  // nextStart did not advance: the reference would repeat this match forever
+    from = e;
+  }
+  p.counts[i] = count;
+}
+
 struct FindAllParams {
   BatchParams b;                  // data, offsets, n, tables, reverse mode (matched/start/end/from unused)
   uint32_t* counts;

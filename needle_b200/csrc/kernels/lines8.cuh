@@ -537,7 +537,9 @@ __device__ __forceinline__ void l8_slow_line(const BatchParams& g, uint64_t i) {
   const uint64_t o0 = batch_off(g, i), o1 = batch_off(g, i + 1);
   const CharT* s = static_cast<const CharT*>(g.data) + o0;
   const int64_t len = static_cast<int64_t>(o1 - o0);
-  if (g.mode == 0) {
+  if (g.mode == kModeFindAll) {
+    dev_find_all_line<CharT>(g, i);
+  } else if (g.mode == 0) {
     g.matched[i] = dev_matches<CharT>(g, s, len);
   } else if (g.mode == 1) {
     g.matched[i] = dev_contained_in<CharT>(g, s, len);
@@ -605,7 +607,9 @@ struct L8Geom {
   static constexpr uint32_t kCopies = kTileLines * kCpl / 32u;                    // cp.async per lane per tile
 };
 
-template <int LOG2CPL, int CM>
+// kOffsets: the batch has an offsets array (ndl_match_batch); false: equally spaced records (ndl_match_lines) - a template
+// parameter so that the per-tile code holds one of the two address computations, not both under predicates.
+template <int LOG2CPL, int CM, bool kOffsets>
 __device__ __forceinline__ void l8_run(const Lines8Params& p, const L8Ctx& cx, const uint32_t buf0, const uint32_t buf1,
                                        const uint32_t lane, const uint32_t warp_global, const uint32_t n_warps) {
   using G = L8Geom<LOG2CPL>;
@@ -631,8 +635,13 @@ __device__ __forceinline__ void l8_run(const Lines8Params& p, const L8Ctx& cx, c
   // offsets (in chars) of line (tile * kTileLines + lane) and the next one
   auto load_offsets = [&](uint32_t tile, uint64_t& o0, uint64_t& o1) {
     const uint32_t i = tile * G::kTileLines + lane_line;
-    o0 = batch_off(g, i);
-    o1 = batch_off(g, i + 1);
+    if constexpr (kOffsets) {
+      o0 = g.offsets[i];
+      o1 = g.offsets[i + 1];
+    } else {
+      o0 = static_cast<uint64_t>(i) * g.line_chars;
+      o1 = o0 + g.line_chars;
+    }
   };
   // Issue the copies of a tile whose offsets are (o0, o1); returns whether the tile is regular.
   auto stage = [&](uint64_t o0, uint64_t o1, uint32_t buf) -> bool {
@@ -1035,15 +1044,165 @@ __device__ __forceinline__ void l8_run_ragged(const Lines8Params& p, const L8Ctx
 }
 
 
+// ---------------------------------------------------------------------------------------------
+// Iterated find() on the staged tile: all non-overlapping matches of every line - the loop
+// `while (m.find()) { m.start(); m.end(); }` (DFACompilerTest.java:678-699), find() resuming at nextStart = end
+// of the previous match and the reverse pass bounded below by it (DFAClassBuilder.java:625-659).  One line per lane,
+// tiles double-buffered as in l8_run; the lane loops over its line's matches, every forward scan starting wherever the
+// last match ended (any byte offset: realigned windows as in the ragged walk), the reverse pass on the same staged bytes.
+// A match that does not move nextStart forward would repeat forever in the reference (:634-635): reported once, ends the line.
+// counts[i] = matches of line i; with match_offsets, match k is stored at match_offsets[i] + k (two-pass CSR).
+// ---------------------------------------------------------------------------------------------
+template <int CM>
+__device__ __forceinline__ void l8_find_all(const Lines8Params& p, const L8Ctx& cx, const uint32_t buf0, const uint32_t buf1,
+                                            const uint32_t lane, const uint32_t warp_global, const uint32_t n_warps) {
+  using CharT = typename std::conditional<L8Chars<CM>::kBytes == 1, uint8_t, uint16_t>::type;
+  constexpr uint32_t kCharBytes = L8Chars<CM>::kBytes;
+  constexpr uint32_t kPer = L8Chars<CM>::kPerChunk;
+  constexpr uint32_t kFull = 0xffffffffu;
+  const BatchParams& g = p.g;
+  const uint8_t* const data = static_cast<const uint8_t*>(g.data);
+  const uint32_t n = static_cast<uint32_t>(g.n);
+  const uint32_t per_warp = (n + n_warps - 1) / n_warps;
+  const uint32_t lo = min(n, warp_global * per_warp), hi = min(n, lo + per_warp);
+  constexpr uint32_t kCap = kL8WarpBuf - 16;  // the last 16 bytes stay free for the window that runs past the tile
+
+  struct Plan {
+    uint32_t count;  // lines in the tile; 0: the next line does not fit a buffer (generic walk)
+    uint32_t start;  // this lane's line: first byte, relative to the tile buffer
+    uint32_t len;    // its length in chars
+  };
+  auto plan_and_stage = [&](uint32_t c, uint32_t buf) -> Plan {
+    Plan pl;
+    pl.count = 0; pl.start = 0; pl.len = 0;
+    if (c < hi) {
+      const uint64_t s0 = batch_off(g, c) * kCharBytes;  // bytes
+      const uint32_t idx = min(c + lane + 1, hi);
+      const uint64_t e_off = batch_off(g, idx) * kCharBytes;
+      const uint32_t slack = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(data) + s0) & 15u;
+      const uint64_t rel_end = e_off - s0 + slack;
+      const bool fits = (c + lane < hi) && rel_end <= kCap;
+      pl.count = __popc(__ballot_sync(kFull, fits));  // offsets are non-decreasing, so `fits` is a prefix
+      if (pl.count) {
+        const uint32_t end32 = static_cast<uint32_t>(rel_end);
+        uint32_t prev = __shfl_up_sync(kFull, end32, 1);
+        if (lane == 0) prev = slack;
+        pl.start = prev;
+        pl.len = (end32 - prev) / kCharBytes;
+        const uint32_t total = __shfl_sync(kFull, end32, pl.count - 1);
+        const uint32_t n_chunks = (total + 15) >> 4;
+        const uint8_t* src = data + s0 - slack;
+        for (uint32_t j = lane; j < n_chunks; j += 32) cp_async16(buf + l8_rslot(j), src + (static_cast<uint64_t>(j) << 4));
+      }
+    }
+    cp_async_commit();
+    return pl;
+  };
+  // matches of line i, handed to the caller's arrays
+  auto emit = [&](uint32_t i, uint32_t k, uint64_t out, uint64_t cap, int32_t st, int32_t en) {
+    (void)i;
+    if (k < cap) {
+      g.start[out + k] = st;
+      g.end[out + k] = en;
+    }
+  };
+  // (lines longer than a tile buffer run the whole loop straight from global memory: dev_find_all_line)
+  auto generic_line = [&](uint32_t i) { dev_find_all_line<CharT>(g, i); };
+
+  uint32_t c = lo, cur = buf0, nxt = buf1;
+  Plan t = plan_and_stage(c, cur);
+  while (c < hi) {
+    if (t.count == 0) {  // a line that does not fit a buffer: it and up to 31 followers take the generic loop, one per lane
+      cp_async_wait<0>();
+      const uint32_t m = min(32u, hi - c);
+      if (lane < m) generic_line(c + lane);
+      __syncwarp();
+      c += m;
+      t = plan_and_stage(c, cur);
+      continue;
+    }
+    const uint32_t cn = c + t.count;
+    const Plan tn = plan_and_stage(cn, nxt);  // (commits a group even when nothing is staged)
+    cp_async_wait<1>();
+    __syncwarp();
+    if (lane < t.count) {
+      const uint32_t i = c + lane;
+      const uint32_t len = t.len;
+      uint64_t out = 0, cap = 0;
+      if (g.match_offsets) {
+        out = g.match_offsets[i];
+        cap = g.match_offsets[i + 1] - out;
+      }
+      auto chunk_addr = [&](uint32_t ch) { return cur + l8_rslot(ch); };
+      uint32_t count = 0, from = 0;
+      for (;;) {
+        // indexForwards(from): DFAClassBuilder.java:335-471
+        int32_t last = g.fwd.root_accepting ? (from < len ? static_cast<int32_t>(from) : 0) : -1;
+        const uint32_t ps = t.start + from * kCharBytes;
+        const L8Align al(ps & 15u);
+        uint32_t ch = ps >> 4, pos = from, e = cx.root;
+        uint4 x = lds_data16(chunk_addr(ch));
+        while (pos < len) {
+          const uint4 y = lds_data16(chunk_addr(++ch));
+          const uint4 wv = al.apply(x, y);
+          uint32_t mask = 0;
+          l8_chunk<CM>(wv, p.q, cx, e, mask);
+          const uint32_t valid = min(kPer, len - pos);
+          mask >>= (kPer - valid);  // drop the accept bits of chars past the end of the line
+          const int32_t cand = static_cast<int32_t>(pos + valid + 1) - __ffs(mask);
+          last = mask ? cand : last;
+          x = y;
+          pos += kPer;
+          if ((e & L8Enc<CM>::kStateMask) == cx.fwd_dead) break;
+        }
+        if (last == -1) break;
+        // start(): DFAClassBuilder.java:640-659, lower bound = from
+        int32_t st;
+        const int32_t rel = last - static_cast<int32_t>(from);
+        if (g.reverse_mode == 2) {
+          st = last - g.min_length;
+        } else if (g.reverse_mode == 0 && p.has_bwd) {
+          st = l8_reverse<CM>(p, chunk_addr, ps, rel, cx, g.bwd.root_accepting != 0);
+          if (st != 0x7fffffff) st += static_cast<int32_t>(from);
+        } else if (g.reverse_mode == 1) {
+          st = l8_reverse_char<CM>(chunk_addr, ps, rel, g.reverse_char);
+          if (st != 0x7fffffff) st += static_cast<int32_t>(from);
+        } else {
+          st = static_cast<int32_t>(dev_index_backwards<CharT>(g, static_cast<const CharT*>(g.data) + batch_off(g, i), last - 1, from, 0x7fffffff));
+        }
+        emit(i, count, out, cap, st, last);
+        count++;
+        if (last <= static_cast<int32_t>(from)) break;  // nextStart did not advance: the reference would repeat this match forever
+        from = static_cast<uint32_t>(last);
+      }
+      g.counts[i] = count;
+    }
+    __syncwarp();  // every lane is done with `cur` before the stage after next overwrites it
+    c = cn;
+    const uint32_t tmp = cur;
+    cur = nxt;
+    nxt = tmp;
+    t = tn;
+  }
+  cp_async_wait<0>();
+}
+
 template <int CM>
 __device__ __forceinline__ void l8_dispatch(const Lines8Params& p, const L8Ctx& cx, int log2cpl, uint32_t buf0, uint32_t buf1,
                                             uint32_t lane, uint32_t warp_global, uint32_t n_warps) {
+  if (p.g.mode == kModeFindAll) {
+    l8_find_all<CM>(p, cx, buf0, buf1, lane, warp_global, n_warps);
+    return;
+  }
+  const bool off = p.g.offsets != nullptr;
   switch (log2cpl) {
-    case 0: l8_run<0, CM>(p, cx, buf0, buf1, lane, warp_global, n_warps); break;
-    case 1: l8_run<1, CM>(p, cx, buf0, buf1, lane, warp_global, n_warps); break;
-    case 2: l8_run<2, CM>(p, cx, buf0, buf1, lane, warp_global, n_warps); break;
-    case 3: l8_run<3, CM>(p, cx, buf0, buf1, lane, warp_global, n_warps); break;
-    case 4: l8_run<4, CM>(p, cx, buf0, buf1, lane, warp_global, n_warps); break;
+#define NDL_RUN(L)                                                               \
+  case L:                                                                        \
+    if (off) l8_run<L, CM, true>(p, cx, buf0, buf1, lane, warp_global, n_warps); \
+    else l8_run<L, CM, false>(p, cx, buf0, buf1, lane, warp_global, n_warps);    \
+    break;
+    NDL_RUN(0) NDL_RUN(1) NDL_RUN(2) NDL_RUN(3) NDL_RUN(4)
+#undef NDL_RUN
     default: l8_run_ragged<CM>(p, cx, buf0, buf1, lane, warp_global, n_warps); break;
   }
 }
