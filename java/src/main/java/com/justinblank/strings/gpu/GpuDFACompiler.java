@@ -1,5 +1,6 @@
 package com.justinblank.strings.gpu;
 
+import com.justinblank.strings.CompilerOptions;
 import com.justinblank.strings.Pattern;
 import com.justinblank.strings.PatternClassCompilationException;
 
@@ -28,6 +29,29 @@ public final class GpuDFACompiler {
         Objects.requireNonNull(className, "name cannot be null");
         byte[] blob = compileToBytes(regex, className, flags);
         return new GpuPattern(blob, /*device=*/0);
+    }
+
+    /**
+     * DFACompiler.compile(String, String, CompilerOptions) (DFACompiler.java:25).  Of the options only the flags reach the
+     * tables: the character distribution steers the reference's choice of search accelerators (recorded in the blob for
+     * the CPU baseline, not used on the GPU) and the debug options print JVM-side artefacts that do not exist here.
+     * CompilerOptions keeps its fields protected, so the flags are read through {@link GpuCompilerOptions}.
+     */
+    public static Pattern compile(String regex, String className, CompilerOptions options) {
+        Objects.requireNonNull(options, "options cannot be null");
+        return compile(regex, className, GpuCompilerOptions.flagsOf(options));
+    }
+
+    /** DFACompiler.compileToBytes(String, String, CompilerOptions) */
+    public static byte[] compileToBytes(String regex, String className, CompilerOptions options) {
+        Objects.requireNonNull(options, "options cannot be null");
+        return compileToBytes(regex, className, GpuCompilerOptions.flagsOf(options));
+    }
+
+    /** Every visible GPU: one replica per device, tables sent with one NCCL broadcast; batches are sharded by the library. */
+    public static Pattern compileOnAllDevices(String regex, String className, int flags) {
+        Objects.requireNonNull(className, "name cannot be null");
+        return new GpuPattern(compileToBytes(regex, className, flags), /*device=*/-1);
     }
 
     /** DFACompiler.compileToBytes: returns the table blob (what Precompile writes to disk). */

@@ -91,6 +91,19 @@ public final class GpuPattern implements Pattern, AutoCloseable {
         return NeedleNative.findAllStrings(handle, haystacks);
     }
 
+    /**
+     * A direct buffer over page-locked memory (ndl_host_alloc) for batch data / offsets: the GPU's copy engine reads it
+     * directly.  Heap or ordinary direct buffers work too - the library then stages them through its own pinned ring.
+     * Release it with {@link #freePinned}.
+     */
+    public static ByteBuffer allocatePinned(long bytes) {
+        return NeedleNative.pinnedAlloc(bytes).order(ByteOrder.LITTLE_ENDIAN);
+    }
+
+    public static void freePinned(ByteBuffer buffer) {
+        NeedleNative.pinnedFree(buffer);
+    }
+
     public byte[] blob() {
         return blob.clone();
     }

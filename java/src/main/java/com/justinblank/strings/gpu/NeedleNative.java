@@ -14,7 +14,8 @@ final class NeedleNative {
     /** ndl_compile; throws PatternSyntaxException / IllegalStateException / RuntimeException per NDL_E* code. */
     static native byte[] compile(String regex, int flags);
 
-    /** ndl_pattern_create; throws RuntimeException("NDL_ECUDA ...") when no GPU is usable (no CPU fallback). */
+    /** ndl_pattern_create (device -1: one replica per visible GPU, tables NCCL-broadcast); throws RuntimeException("NDL_ECUDA ...")
+     *  when no GPU is usable (no CPU fallback). */
     static native long patternCreate(byte[] blob, int device);
 
     static native void patternDestroy(long handle);
@@ -38,6 +39,12 @@ final class NeedleNative {
     static native void findAllBatch(long handle, ByteBuffer data, ByteBuffer offsets, int n, int charWidth, int[] counts,
                                     ByteBuffer matchOffsets, int[] starts, int[] ends);
 
-    /** Packs the strings with GetStringRegion into one pinned staging buffer and runs find() on all of them. */
+    /** Packs the strings with GetStringRegion into one page-locked staging buffer (ndl_host_alloc) and runs find() on all of them. */
     static native GpuPattern.BatchResult findAllStrings(long handle, String[] haystacks);
+
+    /** ndl_host_alloc: a direct ByteBuffer over page-locked memory - batches in it are DMA'd without a bounce copy. */
+    static native ByteBuffer pinnedAlloc(long bytes);
+
+    /** ndl_host_free for a buffer of {@link #pinnedAlloc}; the buffer must not be used afterwards. */
+    static native void pinnedFree(ByteBuffer buffer);
 }

@@ -29,6 +29,9 @@
 namespace ndl {
 
 static std::atomic<uint64_t> g_launches{0};
+// Test hook: how the last chunk-parallel ndl_find_long settled - 1 = the first pass verified, k > 1 = after k - 1 further
+// passes (one repeat that records exits + refinement passes), -1 = gave up: exact sequential walk.
+static std::atomic<int> g_long_passes{0};
 
 #define NDL_CUDA(expr)                                                                             \
   do {                                                                                             \
@@ -101,6 +104,9 @@ struct Workspace {
   uint32_t* seam_exit = nullptr;
   uint32_t* seam_acc = nullptr;
   size_t seam_cap = 0;
+  uint32_t* exit_a = nullptr;  // per-segment exit states of the refinement passes (ping-pong)
+  uint32_t* exit_b = nullptr;
+  size_t exit_cap = 0;
   void* long_scratch = nullptr;
   // pageable callers
   static constexpr int kRing = 3;
@@ -156,6 +162,7 @@ struct ndl_pattern {
   std::mutex ws_mutex;
   Workspace ws;
   bool long8_ready = false;  // long8_kernel's shared-memory attribute is set
+  bool long_refines = false; // the last chunk-parallel find needed refinement passes: the next one records exits from its first pass
   // host-buffer calls are pipelined in chunks: H2D on s_h2d, kernels on the caller's stream, D2H on s_d2h
   static constexpr int kMaxChunks = 16;
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_own = nullptr;
@@ -191,6 +198,8 @@ static void free_pattern(ndl_pattern* p) {
     cudaFree(ws.seam_guess);
     cudaFree(ws.seam_exit);
     cudaFree(ws.seam_acc);
+    cudaFree(ws.exit_a);
+    cudaFree(ws.exit_b);
     cudaFree(ws.long_scratch);
     for (int k = 0; k < Workspace::kRing; k++) {
       if (ws.ring[k]) cudaFreeHost(ws.ring[k]);
@@ -355,6 +364,9 @@ int ndl_device_count(void) {
 }
 
 uint64_t ndl_kernel_launches(void) { return g_launches.load(); }
+
+// Test hook (not in include/needle_b200.h): see g_long_passes.
+int ndl_debug_long_passes(void) { return g_long_passes.load(); }
 
 int ndl_pattern_device(const ndl_pattern* p) { return p ? p->device : -1; }
 
@@ -1215,7 +1227,6 @@ static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, in
           NDL_CUDA(cudaMalloc(&ws.seam_acc, cap * sizeof(uint32_t)));
           ws.seam_cap = cap;
         }
-        NDL_CUDA(cudaMemsetAsync(&d_sc->first_seg, 0xff, 2 * sizeof(unsigned long long), stream));
         Long8Params lp;
         lp.data = d_data + head_end;
         lp.n_segs = n_segs;
@@ -1238,26 +1249,71 @@ static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, in
         const uint32_t block_warps = swar ? kQWarps : kL8Warps;
         uint64_t want = (n_tiles + block_warps - 1) / block_warps;
         int blocks = static_cast<int>(want < static_cast<uint64_t>(p->sm_count) ? want : p->sm_count);
-        kern<<<blocks, block_warps * 32, kL8DynSmem, stream>>>(lp);
-        g_launches.fetch_add(1);
-        NDL_CUDA(cudaGetLastError());
-        long8_seam_kernel<<<p->sm_count * 4, 256, 0, stream>>>(ws.seam_guess, ws.seam_exit, n_tiles, &d_sc->first_bad);
-        g_launches.fetch_add(1);
-        NDL_CUDA(cudaGetLastError());
         Long8Decode dk;
         dk.kind = swar ? 2 : s1 ? 1 : 0;
         dk.row_bytes = row_bytes ? row_bytes : 1;
         dk.w_rows = w_rows;
         dk.entry_bytes = eb;
-        long8_epilogue_kernel<<<1, 32, 0, stream>>>(fwd, d_data, head_end, n, n_segs, r.state, dk, ws.seam_exit, ws.seam_acc, &d_sc->first_seg,
-                                                    &d_sc->first_bad, &d_sc->epi);
-        g_launches.fetch_add(1);
-        NDL_CUDA(cudaGetLastError());
-        NDL_CUDA(cudaMemcpyAsync(&h.epi, &d_sc->epi, sizeof(Long8Epilogue), cudaMemcpyDeviceToHost, stream));
-        NDL_CUDA(cudaStreamSynchronize(stream));
+        // One pass over the segments + the seam check + the epilogue (one host round trip).  entry_in / exit_out: refinement.
+        auto run_pass = [&](const uint32_t* entry_in, uint32_t* exit_out) -> int {
+          NDL_CUDA(cudaMemsetAsync(&d_sc->first_seg, 0xff, 2 * sizeof(unsigned long long), stream));
+          lp.entry_in = entry_in;
+          lp.exit_out = exit_out;
+          kern<<<blocks, block_warps * 32, kL8DynSmem, stream>>>(lp);
+          g_launches.fetch_add(1);
+          NDL_CUDA(cudaGetLastError());
+          long8_seam_kernel<<<p->sm_count * 4, 256, 0, stream>>>(ws.seam_guess, ws.seam_exit, n_tiles, &d_sc->first_bad);
+          g_launches.fetch_add(1);
+          NDL_CUDA(cudaGetLastError());
+          long8_epilogue_kernel<<<1, 32, 0, stream>>>(fwd, d_data, head_end, n, n_segs, r.state, dk, ws.seam_exit, ws.seam_acc, &d_sc->first_seg,
+                                                      &d_sc->first_bad, &d_sc->epi);
+          g_launches.fetch_add(1);
+          NDL_CUDA(cudaGetLastError());
+          NDL_CUDA(cudaMemcpyAsync(&h.epi, &d_sc->epi, sizeof(Long8Epilogue), cudaMemcpyDeviceToHost, stream));
+          NDL_CUDA(cudaStreamSynchronize(stream));
+          return NDL_OK;
+        };
+        auto ensure_exits = [&]() -> int {
+          if (n_segs > ws.exit_cap) {
+            cudaFree(ws.exit_a);
+            cudaFree(ws.exit_b);
+            ws.exit_a = ws.exit_b = nullptr;
+            ws.exit_cap = 0;
+            const size_t cap = n_segs + n_segs / 8 + 1024;
+            NDL_CUDA(cudaMalloc(&ws.exit_a, cap * sizeof(uint32_t)));
+            NDL_CUDA(cudaMalloc(&ws.exit_b, cap * sizeof(uint32_t)));
+            ws.exit_cap = cap;
+          }
+          return NDL_OK;
+        };
+        int passes = 1;
+        const bool recorded = p->long_refines;  // this pattern needed refinement last time: record the exits right away
+        if (recorded && (rc = ensure_exits()) != NDL_OK) return rc;
+        if ((rc = run_pass(nullptr, recorded ? ws.exit_a : nullptr)) != NDL_OK) return rc;
+        p->long_refines = h.epi.status == 1;
         if (h.epi.status == 1) {
-          // a guess was wrong before any match: the pattern remembers further back than the warm-up.
-          // Fall back to the exact sequential walk from the end of the head.
+          // A guess was wrong before any match: the pattern remembers further back than the 16-byte warm-up (`q[a-z ]*7`).
+          // Refine: repeat the pass with every segment entering in the exit state its predecessor had in the previous pass -
+          // exact as soon as the automaton's memory fits the segments covered so far - a bounded number of times.
+          if ((rc = ensure_exits()) != NDL_OK) return rc;
+          uint32_t *prev = ws.exit_a, *next = ws.exit_b;
+          if (!recorded) {
+            if ((rc = run_pass(nullptr, prev)) != NDL_OK) return rc;  // the same guesses, exits recorded
+            passes++;
+          }
+          constexpr int kMaxRefinePasses = 8;
+          for (int pass = 0; pass < kMaxRefinePasses && h.epi.status == 1; pass++) {
+            passes++;
+            if ((rc = run_pass(prev, next)) != NDL_OK) return rc;
+            uint32_t* tmp = prev;
+            prev = next;
+            next = tmp;
+          }
+        }
+        g_long_passes.store(h.epi.status == 1 ? -1 : passes);
+        if (h.epi.status == 1) {
+          // still unverified (an automaton that remembers arbitrarily far back, `a.*c`): the exact sequential walk from
+          // the end of the head
           if ((rc = seq(head_end, n, r.state, head_end, -1, r)) != NDL_OK) return rc;
           last = r.last;
         } else {

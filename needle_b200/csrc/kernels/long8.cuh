@@ -113,6 +113,12 @@ struct Long8Params {
                            // accepting 64-byte piece) << 2 | piece - where the exact re-walk starts
   unsigned long long* first_seg;   // atomicMin: first segment (global index) that saw an accepting state
   unsigned long long* first_bad;   // atomicMin: first segment whose in-warp check failed
+  // Refinement passes (a pattern that remembers further back than the 16-byte warm-up, e.g. `q[a-z ]*7`): instead of
+  // guessing from the warm-up, segment s enters in entry_in[s - 1] - the exit of segment s - 1 in the PREVIOUS pass - and
+  // every segment leaves its exit in exit_out.  The same checks decide whether the pass is exact; each pass extends the
+  // distance the automaton may remember by one segment (256 bytes).  Both NULL: the plain guessing pass.
+  const uint32_t* entry_in;
+  uint32_t* exit_out;
 };
 
 // A lane owns 256 contiguous bytes of a tile and walks them as four 64-byte pieces through the usual swizzled
@@ -203,7 +209,8 @@ __global__ void __launch_bounds__(cm_is_swar(CM) ? kQThreads : kL8Threads, 1) lo
     const uint32_t segs_here = static_cast<uint32_t>(min(static_cast<uint64_t>(32), p.n_segs - seg0));
     const bool act = lane < segs_here;
     // a match in an earlier segment makes this tile - and every later one of this warp - irrelevant
-    if (*reinterpret_cast<volatile unsigned long long*>(p.first_seg) < seg0) {
+    // (not while refining: an accept seen from a wrong entry state must not hide the segments behind it)
+    if (p.exit_out == nullptr && *reinterpret_cast<volatile unsigned long long*>(p.first_seg) < seg0) {
       if (lane == 0)
         for (uint64_t u = t; u < n_tiles; u += n_warps) {
           p.seam_guess[u] = 0xffffffffu;  // skipped: not part of the verified prefix
@@ -213,7 +220,11 @@ __global__ void __launch_bounds__(cm_is_swar(CM) ? kQThreads : kL8Threads, 1) lo
     }
     // warm-up bytes: the 16 bytes before the lane's segment, straight from global memory
     uint4 pre = make_uint4(0, 0, 0, 0);
-    if (act && (seg0 + lane) != 0) pre = *reinterpret_cast<const uint4*>(p.data + (seg0 + lane) * kLongSeg - 16);
+    uint32_t entry_prev = 0;
+    if (act && (seg0 + lane) != 0) {
+      if (p.entry_in) entry_prev = p.entry_in[seg0 + lane - 1];
+      else pre = *reinterpret_cast<const uint4*>(p.data + (seg0 + lane) * kLongSeg - 16);
+    }
     uint32_t e = cx.root, mask = 0, any = 0, guess = 0, acc_at = 0;
 #pragma unroll 1
     for (uint32_t j = 0; j < 4; j++) {
@@ -224,7 +235,8 @@ __global__ void __launch_bounds__(cm_is_swar(CM) ? kQThreads : kL8Threads, 1) lo
       __syncwarp();
       if (act) {
         if (j == 0) {  // 1. guess the entry state
-          l8_chunk<CM>(pre, p.q, cx, e, mask);
+          if (p.entry_in) e = entry_prev + lane_off;  // (canonical encoding + this lane's table copy)
+          else l8_chunk<CM>(pre, p.q, cx, e, mask);
           if (seg0 + lane == 0) e = p.entry0 + lane_off;  // the head was walked exactly
           guess = (e & kStateMask) - lane_off;
         }
@@ -257,6 +269,7 @@ __global__ void __launch_bounds__(cm_is_swar(CM) ? kQThreads : kL8Threads, 1) lo
       if (acc_lanes) atomicMin(p.first_seg, static_cast<unsigned long long>(seg0 + (__ffs(acc_lanes) - 1)));
     }
     if (lane == segs_here - 1) p.seam_exit[t] = exit_state;
+    if (p.exit_out && act) p.exit_out[seg0 + lane] = exit_state;
     if (acc_lanes && lane == static_cast<uint32_t>(__ffs(acc_lanes) - 1)) p.seam_acc[t] = acc_at;
   }
   cp_async_wait<0>();

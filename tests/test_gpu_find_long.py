@@ -103,6 +103,31 @@ def test_long_memory_pattern_falls_back_to_the_exact_walk():
     data[50_000] = ord("q")
     data[150_000] = ord("7")
     assert pat.find_long(data) == oracle_find_long(ora, data) == (True, 50_000, 150_001)
+    from needle_b200 import _lib
+    assert _lib.lib().ndl_debug_long_passes() == -1  # 100 000 chars of memory: refinement gives up after its bounded passes
+
+
+def test_long_memory_pattern_is_refined_when_its_memory_is_bounded():
+    """`q[a-z ]*7` over text whose runs of [a-z ] are a few hundred chars long: the 16-byte warm-up guesses wrong after every
+    'q', but the automaton's memory ends at the next digit or punctuation mark, so a few refinement passes (every segment
+    entering in its predecessor's exit state of the previous pass) make the chunk-parallel scan exact - no single-thread walk."""
+    from needle_b200 import _lib
+    pat, ora = pair("q[a-z ]*7")
+    rng = np.random.default_rng(12)
+    alpha = np.frombuffer(b"abcdefghijklmnopqrstuvwxyz      ", dtype=np.uint8)
+    n = 48 << 20
+    data = alpha[rng.integers(0, len(alpha), size=n)].copy()
+    breaks = rng.integers(0, n, size=n // 300)
+    data[breaks] = np.frombuffer(b".,;:!?0123456", dtype=np.uint8)[rng.integers(0, 13, size=len(breaks))]
+    data[data == ord("7")] = ord("8")  # no match ...
+    assert pat.find_long(data) == oracle_find_long(ora, data) == (False, -1, -1)
+    assert 1 < _lib.lib().ndl_debug_long_passes() <= 10
+    data[n - 5_000_000 + 17] = ord("q")  # ... then one, 40 chars long, deep in the buffer
+    data[n - 5_000_000 + 18:n - 5_000_000 + 57] = ord("e")
+    data[n - 5_000_000 + 57] = ord("7")
+    got = pat.find_long(data)
+    assert got == oracle_find_long(ora, data) and got[0] and got[2] == n - 5_000_000 + 58
+    assert 1 < _lib.lib().ndl_debug_long_passes() <= 10
 
 
 def test_accepting_root_and_utf16():
