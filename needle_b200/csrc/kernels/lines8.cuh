@@ -715,6 +715,108 @@ __device__ __forceinline__ void l8_run(const Lines8Params& p, const L8Ctx& cx, c
   }
 }
 
+// byte offset of 16-byte chunk c of a byte-contiguous tile: the chunk index XOR-swizzled by (chunk >> 3) (ragged tiles, below)
+__device__ __forceinline__ uint32_t l8_rslot(uint32_t c) { return (c ^ ((c >> 3) & 7)) << 4; }
+
+// ---------------------------------------------------------------------------------------------
+// Fixed-length lines whose byte length is a multiple of 16 but not a power of two (48-, 80-, 96-, 112-byte records):
+// the same tile walk with the chunk count per line as a run-time value.  A tile is min(32, 2048 / L) lines; chunk c of
+// the tile (line-major) sits in the XOR-swizzled slot of the ragged layout.  Every tile re-checks that its lines are
+// equally spaced and 16-byte aligned, like l8_run.
+// ---------------------------------------------------------------------------------------------
+template <int CM, bool kOffsets>
+__device__ __forceinline__ void l8_run_any(const Lines8Params& p, const L8Ctx& cx, const uint32_t buf0, const uint32_t buf1,
+                                           const uint32_t lane, const uint32_t warp_global, const uint32_t n_warps, const uint32_t cpl) {
+  using CharT = typename std::conditional<L8Chars<CM>::kBytes == 1, uint8_t, uint16_t>::type;
+  constexpr uint32_t kCharBytes = L8Chars<CM>::kBytes;
+  constexpr uint32_t kPer = L8Chars<CM>::kPerChunk;
+  const BatchParams& g = p.g;
+  const uint8_t* const data = static_cast<const uint8_t*>(g.data);
+  const uint32_t n = static_cast<uint32_t>(g.n);
+  const uint32_t line_bytes = 16u * cpl, len_chars = line_bytes / kCharBytes;
+  const uint32_t tile_lines = min(32u, kL8WarpBuf / line_bytes);
+  const uint32_t tile_chunks = tile_lines * cpl;
+  const uint32_t n_full = n / tile_lines;
+  const bool active = lane < tile_lines;
+  const uint32_t lane_line = active ? lane : 0;
+
+  auto load_offsets = [&](uint32_t tile, uint64_t& o0, uint64_t& o1) {
+    const uint32_t i = tile * tile_lines + lane_line;
+    if constexpr (kOffsets) {
+      o0 = g.offsets[i];
+      o1 = g.offsets[i + 1];
+    } else {
+      o0 = static_cast<uint64_t>(i) * g.line_chars;
+      o1 = o0 + g.line_chars;
+    }
+  };
+  auto stage = [&](uint64_t o0, uint64_t o1, uint32_t buf) -> bool {
+    const uint64_t tile_off = o0 * kCharBytes - static_cast<uint64_t>(lane_line) * line_bytes;  // same on every lane iff regular
+    const uint8_t* src = data + tile_off;
+    const bool ok = (o1 - o0 == len_chars) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    const bool regular = __all_sync(0xffffffffu, ok) != 0;
+    if (regular)
+      for (uint32_t c = lane; c < tile_chunks; c += 32) cp_async16(buf + l8_rslot(c), src + 16 * c);
+    cp_async_commit();
+    return regular;
+  };
+
+  uint32_t t = warp_global;
+  uint32_t cur = buf0, nxt = buf1;
+  bool regular = false;
+  uint64_t a0 = 0, a1 = 0;  // offsets of the tile after the current one
+  if (t < n_full) {
+    load_offsets(t, a0, a1);
+    regular = stage(a0, a1, cur);
+    if (t + n_warps < n_full) load_offsets(t + n_warps, a0, a1);
+  }
+  for (; t < n_full; t += n_warps) {
+    bool regular_next = false;
+    if (t + n_warps < n_full) {
+      regular_next = stage(a0, a1, nxt);
+      if (t + 2 * n_warps < n_full) load_offsets(t + 2 * n_warps, a0, a1);
+    } else {
+      cp_async_commit();
+    }
+    cp_async_wait<1>();
+    __syncwarp();
+    const uint32_t i = t * tile_lines + lane;
+    if (regular) {
+      if (active) {
+        const uint32_t c0 = lane * cpl;
+        uint32_t e = cx.root;
+        int32_t last = g.fwd.root_accepting ? 0 : -1;
+        uint32_t mask = 0;
+        constexpr uint32_t kFlush = 32 / kPer;  // chunks whose accept bits fit in the 32-bit mask
+        for (uint32_t c = 0; c < cpl; c++) {
+          const uint4 w = lds_data16(cur + l8_rslot(c0 + c));
+          l8_chunk<CM>(w, p.q, cx, e, mask);
+          if ((c % kFlush) == kFlush - 1 || c + 1 == cpl) {  // bit 0 = the most recent char
+            const int32_t cand = static_cast<int32_t>((c + 1) * kPer + 1) - __ffs(mask);
+            last = mask ? cand : last;
+            mask = 0;
+          }
+        }
+        l8_finish<CM, CharT>(p, cx, i, len_chars, last, (e & L8Enc<CM>::kTailFlag) != 0, 0u,
+                             [&](uint32_t ch) { return cur + l8_rslot(c0 + min(ch, cpl - 1)); });
+      }
+    } else if (active) {
+      l8_slow_line<CharT>(g, i);
+    }
+    __syncwarp();  // every lane is done with `cur` before the stage after next overwrites it
+    regular = regular_next;
+    const uint32_t tmp = cur;
+    cur = nxt;
+    nxt = tmp;
+  }
+  cp_async_wait<0>();
+  // the partial last tile
+  if (warp_global == 0) {
+    const uint32_t i = n_full * tile_lines + lane;
+    if (i < n && lane < tile_lines) l8_slow_line<CharT>(g, i);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Ragged lines.  A warp tile is the longest run of <= 32 consecutive lines whose bytes (from the 16-byte
 // boundary below the first line) fit in a 2 KB buffer; chunks are stored XOR-swizzled by (chunk >> 3) so that
@@ -729,7 +831,6 @@ __device__ __forceinline__ void l8_run(const Lines8Params& p, const L8Ctx& cx, c
 // by the k-th longest of the second in ONE loop - the sums are nearly equal across lanes (82 %).  The copies
 // of a pair of tiles are not overlapped with its walk; the other warps of the SM cover them.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t l8_rslot(uint32_t c) { return (c ^ ((c >> 3) & 7)) << 4; }
 
 // ascending bitonic sort of one key per lane
 __device__ __forceinline__ uint32_t warp_sort32(uint32_t key, uint32_t lane) {
@@ -1187,6 +1288,9 @@ __device__ __forceinline__ void l8_find_all(const Lines8Params& p, const L8Ctx& 
   cp_async_wait<0>();
 }
 
+// log2cpl: >= 0 fixed-length lines of 16 << log2cpl bytes; kCplAny + cpl: fixed-length lines of 16 * cpl bytes (not a power of
+// two); -1: ragged.
+constexpr int kCplAny = 100;
 template <int CM>
 __device__ __forceinline__ void l8_dispatch(const Lines8Params& p, const L8Ctx& cx, int log2cpl, uint32_t buf0, uint32_t buf1,
                                             uint32_t lane, uint32_t warp_global, uint32_t n_warps) {
@@ -1195,6 +1299,11 @@ __device__ __forceinline__ void l8_dispatch(const Lines8Params& p, const L8Ctx& 
     return;
   }
   const bool off = p.g.offsets != nullptr;
+  if (log2cpl >= kCplAny) {
+    if (off) l8_run_any<CM, true>(p, cx, buf0, buf1, lane, warp_global, n_warps, static_cast<uint32_t>(log2cpl - kCplAny));
+    else l8_run_any<CM, false>(p, cx, buf0, buf1, lane, warp_global, n_warps, static_cast<uint32_t>(log2cpl - kCplAny));
+    return;
+  }
   switch (log2cpl) {
 #define NDL_RUN(L)                                                               \
   case L:                                                                        \
@@ -1261,6 +1370,7 @@ __global__ void __launch_bounds__(kL8Threads, 1) lines8_kernel(const Lines8Param
   const uint64_t L64 = l_chars * char_bytes;
   int log2cpl = -1;
   if (L64 >= 16 && L64 <= 256 && (L64 & (L64 - 1)) == 0) log2cpl = 31 - __clz(static_cast<uint32_t>(L64)) - 4;
+  else if (L64 > 16 && L64 <= 128 && (L64 & 15) == 0) log2cpl = kCplAny + static_cast<int>(L64 >> 4);  // 48, 80, 96, 112 bytes
   if (layout_ok) mbar_wait(kL8AbsBar, 0);  // table image has landed
 
   const uint32_t warp_global = blockIdx.x * su.usable_warps + warp;
@@ -1341,6 +1451,7 @@ __global__ void __launch_bounds__(kQThreads, 1) linesq_kernel(const Lines8Params
   const uint64_t L64 = l_chars * L8Chars<CM>::kBytes;
   int log2cpl = -1;
   if (L64 >= 16 && L64 <= 256 && (L64 & (L64 - 1)) == 0) log2cpl = 31 - __clz(static_cast<uint32_t>(L64)) - 4;
+  else if (L64 > 16 && L64 <= 128 && (L64 & 15) == 0) log2cpl = kCplAny + static_cast<int>(L64 >> 4);  // 48, 80, 96, 112 bytes
   if (g.from != nullptr && g.mode == 2) log2cpl = -1;  // find(from, to): the ragged walk takes the per-line start offsets
   if (log2cpl >= 0) {
     const uint32_t probe = static_cast<uint32_t>(min(static_cast<uint64_t>(lane) + 1, g.n - 1));

@@ -119,7 +119,7 @@ def test_c2_ssn_fixed_lines(n):
     assert np.all((e - s)[m == 1] == 11)  # fixed-length pattern: start = end - 11
 
 
-@pytest.mark.parametrize("line_len", [16, 32, 64, 128, 48, 80, 256, 11, 1])
+@pytest.mark.parametrize("line_len", [16, 32, 64, 128, 48, 80, 96, 112, 144, 256, 11, 1])
 def test_fixed_lines_all_lengths(line_len):
     rng = np.random.default_rng(line_len)
     n = 5000
@@ -128,6 +128,11 @@ def test_fixed_lines_all_lengths(line_len):
     offsets = np.arange(n + 1, dtype=np.uint64) * np.uint64(line_len)
     for regex in (workloads.REGEX["c2"], r"[0-9]+", r"a*", r"(ab|a|b-)+", r"\d+-\d+"):
         assert_batch_equal(regex, 0, data, offsets)
+    # a line count that is not a multiple of the tile, one irregular line in the middle, a base that is not 16-byte aligned
+    off2 = offsets[:4001].copy()
+    off2[2000:] += 3
+    assert_batch_equal(r"\d+-\d+", 0, data, off2)
+    assert_batch_equal(workloads.REGEX["c3"], 0, data[5:], offsets[:4000])
 
 
 def test_unaligned_base_and_sub_batches():
@@ -384,7 +389,7 @@ def test_find_all_batch_count_only_and_short_capacity():
     assert list(zip(starts.tolist(), ends.tolist())) == [(0, 1), (2, 4), (5, 8), (9, 13), (0, 1)]
 
 
-@pytest.mark.parametrize("line_chars", [64, 16, 256, 40, 11, 0])
+@pytest.mark.parametrize("line_chars", [64, 16, 256, 40, 48, 80, 96, 112, 11, 0])
 def test_match_lines_equals_match_batch_with_computed_offsets(line_chars):
     """ndl_match_lines (fixed-length records, no offsets array) against ndl_match_batch and the oracle."""
     rng = np.random.default_rng(line_chars)
