@@ -274,7 +274,7 @@ def measured_traffic(workload, n):
                 t = json.load(f)[workload]
             if int(t.get("lines", n)) != n:
                 continue
-            return t["dram_bytes_read"] + t["dram_bytes_write"], f"static: profiles/{fn} (ncu --set full of this kernel, {t.get('source', 'same workload and size')})"
+            return t["dram_bytes_read"] + t["dram_bytes_write"], f"static: profiles/{fn} (ncu capture of this kernel at this size: {t.get('source', 'same workload and size')})"
         except Exception:
             continue
     return None, None
