@@ -31,6 +31,7 @@ namespace ndl {
 static std::atomic<uint64_t> g_launches{0};
 // Test hook: how the last chunk-parallel ndl_find_long settled - 1 = the first pass verified, k > 1 = after k - 1 further
 // passes (one repeat that records exits + refinement passes), -1 = gave up: exact sequential walk.
+static std::atomic<int> g_debug_replicas{0};
 static std::atomic<int> g_long_passes{0};
 
 #define NDL_CUDA(expr)                                                                             \
@@ -168,6 +169,7 @@ struct ndl_pattern {
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_own = nullptr;
   cudaEvent_t ev_start = nullptr, ev_h2d[kMaxChunks] = {}, ev_kernel[kMaxChunks] = {};
   std::vector<ndl_pattern*> replicas;
+  std::mutex multi_mutex;  // a multi-device pattern runs one call at a time (its replicas' workspaces hold the call's data)
 };
 
 namespace ndl {
@@ -367,6 +369,9 @@ uint64_t ndl_kernel_launches(void) { return g_launches.load(); }
 
 // Test hook (not in include/needle_b200.h): see g_long_passes.
 int ndl_debug_long_passes(void) { return g_long_passes.load(); }
+// Tests on a one-GPU box: ndl_pattern_create(device = -1) builds `n` replicas on GPU 0 (n < 2: off), so the sharding code of the
+// multi-device paths runs there too.
+void ndl_debug_force_replicas(int n) { g_debug_replicas.store(n); }
 
 int ndl_pattern_device(const ndl_pattern* p) { return p ? p->device : -1; }
 
@@ -711,7 +716,8 @@ int ndl_pattern_create(const uint8_t* blob, size_t blob_len, int device, ndl_pat
   }
   if (device < -1 || device >= count) return fail(NDL_EINVAL, "device ordinal out of range (-1 = every visible device)");
   build_host_pattern(hp);
-  if (device >= 0 || count == 1) {
+  const int forced = device == -1 ? g_debug_replicas.load() : 0;  // tests: several replicas on GPU 0 (no NCCL involved)
+  if (device >= 0 || (count == 1 && forced < 2)) {
     const int dev = device >= 0 ? device : 0;
     ndl_pattern* p = nullptr;
     int rc = instantiate_pattern(hp, dev, &p);
@@ -731,14 +737,26 @@ int ndl_pattern_create(const uint8_t* blob, size_t blob_len, int device, ndl_pat
   root->cp = hp.cp;
   root->device = -1;
   for (int k = 0; k < 4; k++) root->tables[k].host = hp.tables[k];
-  for (int d = 0; d < count; d++) {
+  const int n_replicas = forced >= 2 ? forced : count;
+  for (int d = 0; d < n_replicas; d++) {
     ndl_pattern* r = nullptr;
-    int rc = instantiate_pattern(hp, d, &r);
+    int rc = instantiate_pattern(hp, forced >= 2 ? 0 : d, &r);
     if (rc != NDL_OK) {
       free_pattern(root);
       return rc;
     }
     root->replicas.push_back(r);
+  }
+  if (forced >= 2) {
+    DeviceGuard guard(0);
+    for (ndl_pattern* r : root->replicas)
+      if (cudaMemcpy(r->arena, hp.arena.host.data(), hp.arena.host.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        const std::string why = cudaGetErrorString(cudaGetLastError());
+        free_pattern(root);
+        return fail(NDL_ECUDA, "uploading the table arena failed: " + why);
+      }
+    *out = root;
+    return NDL_OK;
   }
   {
     DeviceGuard guard(0);
@@ -884,6 +902,7 @@ static int match_multi(ndl_pattern* p, int mode, const void* data, const uint64_
   if (mem_kind != NDL_MEM_HOST) return fail(NDL_EINVAL, "a multi-device pattern takes host buffers (device memory belongs to one GPU)");
   if (stream_) return fail(NDL_EINVAL, "a multi-device pattern takes no stream (a stream belongs to one GPU)");
   if (offsets && offsets[0] > offsets[n]) return fail(NDL_EINVAL, "offsets must be non-decreasing");
+  std::lock_guard<std::mutex> multi_lock(p->multi_mutex);
   const int g = static_cast<int>(p->replicas.size());
   std::vector<uint64_t> bounds(g + 1, n);
   bounds[0] = 0;
@@ -1112,7 +1131,7 @@ struct LongScratch { SeqResult r; unsigned long long first_seg, first_bad; int64
 
 static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, int char_width, int64_t from, int32_t entry_state,
                           int64_t last_init, uint8_t* matched, int64_t* start, int64_t* end, int32_t* exit_state, int mem_kind,
-                          void* stream_) {
+                          void* stream_, bool host_results = false) {  // host_results: device haystack, results to host pointers
   if (!p) return fail(NDL_EINVAL, "pattern must not be NULL");
   if (char_width != 1 && char_width != 2) return fail(NDL_EINVAL, "char_width must be 1 or 2");
   if (mem_kind != NDL_MEM_HOST && mem_kind != NDL_MEM_DEVICE) return fail(NDL_EINVAL, "mem_kind must be NDL_MEM_HOST or NDL_MEM_DEVICE");
@@ -1131,7 +1150,11 @@ static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, in
   if (mem_kind == NDL_MEM_HOST) {
     int rc = ensure_workspace(p->ws, static_cast<size_t>(n_chars) * char_width + 64, 16, false, true);
     if (rc != NDL_OK) return rc;
-    if (n_chars) NDL_CUDA(cudaMemcpyAsync(p->ws.data, data, static_cast<size_t>(n_chars) * char_width, cudaMemcpyHostToDevice, stream));
+    if (n_chars) {
+      const bool pinned = host_is_pinned(data);
+      if (!pinned && (rc = ensure_ring(p->ws)) != NDL_OK) return rc;
+      if ((rc = h2d_copy(p->ws, p->ws.data, data, static_cast<size_t>(n_chars) * char_width, pinned, stream)) != NDL_OK) return rc;
+    }
     d_data = static_cast<const uint8_t*>(p->ws.data);
   }
   // scratch: SeqResult + 2 atomics + back result (kept with the pattern; calls are serialised by ws_mutex)
@@ -1358,7 +1381,7 @@ static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, in
   }
   const uint8_t m = last != -1;
   if (exit_state) *exit_state = r.state;  // state after the last char that was read (DEAD when the walk died)
-  if (mem_kind == NDL_MEM_HOST) {
+  if (mem_kind == NDL_MEM_HOST || host_results) {
     *matched = m;
     if (start) *start = st;
     *end = last;
@@ -1371,10 +1394,135 @@ static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, in
   return NDL_OK;
 }
 
+// ndl_find_long on a multi-device pattern (host haystack): the protocol of needle_b200/sharding.py inside the library.  The haystack
+// is cut into one contiguous chunk per GPU; every replica thread copies its chunk over its own link and scans it from a GUESSED entry
+// state (the walk, from the root, of the 16 chars before the chunk - done on the host, the haystack is here); the records (entry,
+// end, exit) are then resolved in order from the root: a record whose entry is not the exit of the verified record before it is
+// scanned again from the now known state (the chunk is still on its GPU).  The end of the match is the last accepting index on the
+// verified path (indexForwards, DFAClassBuilder.java:335-471); the reverse pass (indexBackwards, :529-614) starts on the replica that
+// holds end - 1 and is handed down for as long as the BACKWARDS automaton is alive at a chunk boundary.
+static int find_long_multi(ndl_pattern* root, const void* data, uint64_t n_chars, int char_width, int64_t from, uint8_t* matched,
+                           int64_t* start, int64_t* end, int mem_kind, void* stream_) {
+  if (char_width != 1 && char_width != 2) return fail(NDL_EINVAL, "char_width must be 1 or 2");
+  if (mem_kind != NDL_MEM_HOST) return fail(NDL_EINVAL, "a multi-device pattern takes host buffers (device memory belongs to one GPU)");
+  if (stream_) return fail(NDL_EINVAL, "a multi-device pattern takes no stream (a stream belongs to one GPU)");
+  if (!matched || !start || !end) return fail(NDL_EINVAL, "matched, start and end must not be NULL");
+  if (from < 0) return fail(NDL_EINVAL, "from must be >= 0");
+  std::lock_guard<std::mutex> multi_lock(root->multi_mutex);
+  const int64_t n = static_cast<int64_t>(n_chars);
+  const int g = static_cast<int>(root->replicas.size());
+  constexpr int64_t kMinChunk = 1 << 20;  // below a MiB per GPU the split costs more than it saves
+  if (g < 2 || n - from < g * kMinChunk)
+    return find_long_impl(root->replicas[0], data, n_chars, char_width, from, 0, -1, matched, start, end, nullptr, NDL_MEM_HOST, nullptr);
+
+  const HostDeviceTable& fwd = root->tables[kForwards].host;
+  const int32_t fwd_dead = fwd.n_states, bwd_dead = root->tables[kBackwards].host.n_states;
+  const uint8_t* const bytes = static_cast<const uint8_t*>(data);
+  auto char_at = [&](int64_t i) -> uint32_t {
+    return char_width == 1 ? bytes[i] : reinterpret_cast<const uint16_t*>(bytes)[i];
+  };
+  std::vector<int64_t> b(g + 1);
+  for (int k = 0; k <= g; k++) b[k] = k == g ? n : (from + (n - from) / g * k) & ~static_cast<int64_t>(255) ;
+  b[0] = from;
+  for (int k = 1; k <= g; k++) if (b[k] < b[k - 1]) b[k] = b[k - 1];
+
+  struct Rec {
+    int32_t entry = 0, exit = 0;
+    int64_t end_local = -1;
+    int rc = NDL_OK;
+    std::string msg;
+  };
+  std::vector<Rec> rec(g);
+  const bool pinned = host_is_pinned(data);
+  auto scan = [&](int k, int32_t entry, bool stage) {
+    ndl_pattern* rep = root->replicas[k];
+    Rec& r = rec[k];
+    r.entry = entry;
+    const int64_t len = b[k + 1] - b[k];
+    if (len == 0 && k > 0) {  // (replica 0 always scans: an accepting root matches the empty haystack, :356)
+      r.end_local = -1;
+      r.exit = entry;
+      return;
+    }
+    auto body = [&]() -> int {
+      DeviceGuard guard(rep->device);
+      NDL_DEVICE(guard);
+      if (!rep->s_own) NDL_CUDA(cudaStreamCreateWithFlags(&rep->s_own, cudaStreamNonBlocking));
+      if (stage) {
+        std::lock_guard<std::mutex> lock(rep->ws_mutex);
+        int rc = ensure_workspace(rep->ws, static_cast<size_t>(len) * char_width + 64, 16, false, true);
+        if (rc != NDL_OK) return rc;
+        if (!pinned && (rc = ensure_ring(rep->ws)) != NDL_OK) return rc;
+        rc = h2d_copy(rep->ws, rep->ws.data, bytes + static_cast<size_t>(b[k]) * char_width, static_cast<size_t>(len) * char_width, pinned,
+                      rep->s_own);
+        if (rc != NDL_OK) return rc;
+      }
+      uint8_t m = 0;
+      return find_long_impl(rep, rep->ws.data, static_cast<uint64_t>(len), char_width, 0, entry, -1, &m, nullptr, &r.end_local, &r.exit,
+                            NDL_MEM_DEVICE, rep->s_own, true);
+    };
+    r.rc = body();
+    if (r.rc != NDL_OK) r.msg = ndl_last_error();
+  };
+  // round 0: every replica at once, entry states guessed from the 16-char halo
+  {
+    std::vector<std::thread> threads;
+    auto guess = [&](int k) -> int32_t {
+      int32_t s = 0;
+      for (int64_t i = std::max(from, b[k] - 16); i < b[k]; i++) s = fwd.trans[static_cast<size_t>(s) * fwd.n_classes + fwd.cmap[char_at(i)]];
+      return s;
+    };
+    for (int k = 1; k < g; k++) threads.emplace_back([&, k] { scan(k, guess(k), true); });
+    scan(0, 0, true);
+    for (auto& t : threads) t.join();
+  }
+  for (int k = 0; k < g; k++)
+    if (rec[k].rc != NDL_OK) return fail(rec[k].rc, "GPU " + std::to_string(root->replicas[k]->device) + ": " + rec[k].msg);
+  // resolve in order; a wrong guess is scanned again from the true state
+  int32_t state = 0;
+  int64_t last = -1;
+  for (int k = 0; k < g && state != fwd_dead; k++) {
+    if (rec[k].entry != state) {
+      scan(k, state, false);
+      if (rec[k].rc != NDL_OK) return fail(rec[k].rc, "GPU " + std::to_string(root->replicas[k]->device) + ": " + rec[k].msg);
+    }
+    if (rec[k].end_local != -1) last = b[k] + rec[k].end_local;
+    state = rec[k].exit;
+  }
+  *matched = last != -1;
+  *end = last;
+  *start = -1;
+  if (last == -1) return NDL_OK;
+  if (root->cp.reverse_mode == kReverseFixedLength) {
+    *start = last - root->cp.min_length;
+    return NDL_OK;
+  }
+  // reverse pass, handed down replica by replica
+  const int64_t kNoStart = INT64_MAX;
+  int32_t bstate = 0;
+  int64_t st = (root->tables[kBackwards].host.root_accepting && root->cp.reverse_mode == 0) ? from : kNoStart;
+  int64_t index = last - 1;
+  for (int k = g - 1; k >= 0 && index >= from; k--) {
+    const int64_t len = b[k + 1] - b[k];
+    if (len == 0 || index < b[k] || index >= b[k + 1]) continue;
+    ndl_pattern* rep = root->replicas[k];
+    int64_t s_local = kNoStart;
+    const int rc = ndl_find_long_back(rep, rep->ws.data, static_cast<uint64_t>(len), char_width, index - b[k], 0, bstate,
+                                      st == kNoStart ? kNoStart : st - b[k], &s_local, &bstate, NDL_MEM_DEVICE, rep->s_own);
+    if (rc != NDL_OK) return rc;
+    st = s_local == kNoStart ? kNoStart : s_local + b[k];
+    index = b[k] - 1;
+    if (bstate == bwd_dead) break;
+  }
+  *start = st;
+  return NDL_OK;
+}
+
 extern "C" {
 
 int ndl_find_long(ndl_pattern* p, const void* data, uint64_t n_chars, int char_width, int64_t from, uint8_t* matched,
                   int64_t* start, int64_t* end, int mem_kind, void* stream) {
+  if (p && p->device < 0) return find_long_multi(p, data, n_chars, char_width, from, matched, start, end, mem_kind, stream);
   return find_long_impl(p, data, n_chars, char_width, from, 0, -1, matched, start, end, nullptr, mem_kind, stream);
 }
 

@@ -7,6 +7,7 @@
 #include "host/ast.h"
 #include "host/pattern.h"
 #include "host_chunks.h"
+#include "host_staging.h"
 #include "needle_b200.h"
 
 namespace ndl {
@@ -179,6 +180,23 @@ extern "C" int ndl_debug_plan_chunks(const uint64_t* offsets, uint64_t line_char
     i0 = i1;
   }
   return used;
+}
+
+// Test hook (not part of include/needle_b200.h; host only): `callers` threads copy disjoint slices of src to dst through the copy
+// pool AT THE SAME TIME - what the replica threads of a multi-device pattern do with pageable input.  Returns the pool's threads.
+extern "C" int ndl_debug_parallel_copy(uint8_t* dst, const uint8_t* src, uint64_t bytes, int callers) {
+  if (callers < 1) callers = 1;
+  std::vector<std::thread> threads;
+  const uint64_t slice = (bytes + callers - 1) / callers;
+  for (int k = 0; k < callers; k++) {
+    const uint64_t lo = std::min(bytes, slice * k), hi = std::min(bytes, lo + slice);
+    threads.emplace_back([=] {
+      for (uint64_t off = lo; off < hi; off += 5u << 20)  // ring-sized pieces, as h2d_copy issues them
+        ndl::CopyPool::instance().copy(dst + off, src + off, static_cast<size_t>(std::min<uint64_t>(5u << 20, hi - off)));
+    });
+  }
+  for (auto& t : threads) t.join();
+  return ndl::CopyPool::instance().threads();
 }
 
 // Test hook (not part of include/needle_b200.h): the byte classes EACH of the four automata of a pattern would have on

@@ -33,22 +33,23 @@ class CopyPool {
       std::memcpy(dst, src, bytes);
       return;
     }
-    std::lock_guard<std::mutex> call_lock(call_mutex_);  // one parallel copy at a time
+    // several callers (the replica threads of a multi-device pattern) may copy at once: every call counts its own pieces
     const size_t piece = ((bytes / static_cast<size_t>(pieces)) + 4095) & ~static_cast<size_t>(4095);
+    int pending = 0;
     {
       std::lock_guard<std::mutex> lock(mutex_);
       for (int k = 1; k < pieces; k++) {
         const size_t lo = std::min(bytes, piece * static_cast<size_t>(k)), hi = std::min(bytes, lo + piece);
         if (hi > lo) {
-          jobs_.push_back({static_cast<uint8_t*>(dst) + lo, static_cast<const uint8_t*>(src) + lo, hi - lo});
-          pending_++;
+          jobs_.push_back({static_cast<uint8_t*>(dst) + lo, static_cast<const uint8_t*>(src) + lo, hi - lo, &pending});
+          pending++;
         }
       }
     }
     wake_.notify_all();
     std::memcpy(dst, src, std::min(bytes, piece));  // the calling thread takes the first piece
     std::unique_lock<std::mutex> lock(mutex_);
-    done_.wait(lock, [&] { return pending_ == 0; });
+    done_.wait(lock, [&] { return pending == 0; });
   }
 
  private:
@@ -56,10 +57,11 @@ class CopyPool {
     uint8_t* dst;
     const uint8_t* src;
     size_t bytes;
+    int* pending;  // the call's count of unfinished pieces (guarded by mutex_)
   };
   CopyPool() {
     unsigned hw = std::thread::hardware_concurrency();
-    int n = static_cast<int>(hw ? std::min(hw, 8u) : 4u) - 1;
+    int n = static_cast<int>(hw ? std::min(hw, 16u) : 4u) - 1;
     for (int i = 0; i < n; i++) workers_.emplace_back([this] { run(); });
   }
   ~CopyPool() {
@@ -83,15 +85,14 @@ class CopyPool {
       std::memcpy(j.dst, j.src, j.bytes);
       {
         std::lock_guard<std::mutex> lock(mutex_);
-        if (--pending_ == 0) done_.notify_all();
+        if (--*j.pending == 0) done_.notify_all();
       }
     }
   }
   std::vector<std::thread> workers_;
   std::vector<Job> jobs_;
-  std::mutex mutex_, call_mutex_;
+  std::mutex mutex_;
   std::condition_variable wake_, done_;
-  int pending_ = 0;
   bool stop_ = false;
 };
 

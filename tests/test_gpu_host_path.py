@@ -112,3 +112,84 @@ def test_multi_device_pattern_shards_the_batch():
         t = torch.zeros(64, dtype=torch.uint8, device="cuda:0")
         with pytest.raises(RuntimeError):
             pat.match_batch_ptrs(2, t.data_ptr(), t.data_ptr(), 1, 1, t.data_ptr(), t.data_ptr(), t.data_ptr())
+
+
+def _oracle_find_long(ora, data, from_=0, cw=1):
+    import ctypes
+    from tests.oracle_lib import INT64_MAX, lib as oracle_lib
+    st, en = ctypes.c_int64(), ctypes.c_int64()
+    data = np.ascontiguousarray(data).view(np.uint8)
+    m = oracle_lib().ndlo_find(ora._h, data.ctypes.data, data.size // cw, cw, from_, INT64_MAX, ctypes.byref(st), ctypes.byref(en))
+    return bool(m), st.value, en.value
+
+
+@pytest.fixture
+def three_replicas():
+    """ndl_pattern_create(device = -1) builds three replicas on GPU 0: the sharding code of the multi-device paths runs on a one-GPU box."""
+    L = _lib.lib()
+    L.ndl_debug_force_replicas(3)
+    try:
+        yield 3
+    finally:
+        L.ndl_debug_force_replicas(0)
+
+
+def test_replicas_shard_a_batch(three_replicas):
+    L = _lib.lib()
+    blob = nb.compile_to_bytes(SSN, 0)
+    pat, ora = nb.Pattern(blob, device=-1), Oracle(blob)
+    assert L.ndl_pattern_device_count(pat._h) == 3
+    data, offsets = workloads.c2_lines(300_000)
+    check(pat, ora, data, offsets)
+    d3, o3 = workloads.c3_lines(200_000)
+    blob3 = nb.compile_to_bytes(workloads.REGEX["c3"], 0)
+    check(nb.Pattern(blob3, device=-1), Oracle(blob3), d3, o3)
+
+
+def test_replicas_split_one_long_haystack(three_replicas):
+    """ndl_find_long on a multi-device pattern: chunk per replica, guessed entry states, in-order resolution with re-scans, reverse pass
+    handed down across chunk boundaries - against the oracle's sequential walk."""
+    n = 12 << 20
+    rng = np.random.default_rng(11)
+    ab = (rng.integers(0, 2, size=n, dtype=np.uint8) + ord("a")).astype(np.uint8)
+    cut1, cut2 = (n // 3) & ~255, (2 * (n // 3)) & ~255  # the chunk boundaries of find_long_multi for from = 0
+
+    # fixed-length pattern (BASELINE config 4): no match, match at the end, match across a boundary, from > 0
+    blob = nb.compile_to_bytes(workloads.REGEX["c4"], 0)
+    pat, ora = nb.Pattern(blob, device=-1), Oracle(blob)
+    assert pat.find_long(ab) == _oracle_find_long(ora, ab) == (False, -1, -1)
+    for pos in (n - 9, cut1 - 4, cut2 - 8, cut2, 5, cut1 + 100_000):
+        data = ab.copy()
+        data[pos], data[pos + 8] = ord("a"), ord("c")
+        assert pat.find_long(data) == _oracle_find_long(ora, data) == (True, pos, pos + 9), pos
+    data = ab.copy()
+    for pos in (1000, cut2 + 77):
+        data[pos], data[pos + 8] = ord("a"), ord("c")
+    assert pat.find_long(data, from_=1001) == _oracle_find_long(ora, data, 1001) == (True, cut2 + 77, cut2 + 86)
+    assert pat.find_long(data, from_=n - 5) == _oracle_find_long(ora, data, n - 5)
+
+    # variable-length patterns: reverse pass on the tables, matches that straddle a boundary, automata that remember across it
+    text = np.frombuffer(bytes(rng.choice(list(b"abcdefghij klmnop"), size=n).astype(np.uint8)), dtype=np.uint8).copy()
+    for regex in (r"q[a-z ]*7", r"[0-9]+x", r"Sherlock|Street"):
+        blob = nb.compile_to_bytes(regex, 0)
+        pat, ora = nb.Pattern(blob, device=-1), Oracle(blob)
+        assert pat.find_long(text) == _oracle_find_long(ora, text) == (False, -1, -1), regex
+    blob = nb.compile_to_bytes(r"q[a-z ]*7", 0)
+    pat, ora = nb.Pattern(blob, device=-1), Oracle(blob)
+    for q, seven in ((cut1 - 50, cut1 + 50), (cut1 - 3_000_000, cut2 + 10), (100, n - 1), (cut2 - 1, cut2)):
+        data = text.copy()
+        data[q], data[seven] = ord("q"), ord("7")
+        assert pat.find_long(data) == _oracle_find_long(ora, data) == (True, q, seven + 1), (q, seven)
+    blob = nb.compile_to_bytes(r"[0-9]+x", 0)
+    pat, ora = nb.Pattern(blob, device=-1), Oracle(blob)
+    data = text.copy()
+    data[cut1 - 20:cut1 + 30] = ord("5")
+    data[cut1 + 30] = ord("x")
+    assert pat.find_long(data) == _oracle_find_long(ora, data) == (True, cut1 - 20, cut1 + 31)
+
+    # UTF-16 haystack, pageable memory (the pinned ring stages it)
+    wide = text[: 4 << 20].astype(np.uint16)
+    blob = nb.compile_to_bytes(r"q[a-z ]*7", 0)
+    pat, ora = nb.Pattern(blob, device=-1), Oracle(blob)
+    wide[(4 << 20) // 3 - 10], wide[(4 << 20) // 3 + 500] = ord("q"), ord("7")
+    assert pat.find_long(wide, char_width=2) == _oracle_find_long(ora, wide, cw=2)

@@ -87,3 +87,17 @@ def test_more_chunks_than_lines():
     offsets = np.array([0, 1 << 30, 2 << 30], dtype=np.uint64)
     bounds, _ = plan(offsets, 2)
     assert bounds == [0, 1, 2]
+
+
+def test_copy_pool_serves_concurrent_callers():
+    """The pinned-ring staging of pageable input (host_staging.h) is used by all replica threads of a multi-device pattern at once."""
+    import ctypes
+    L = _lib.lib()
+    L.ndl_debug_parallel_copy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int]
+    rng = np.random.default_rng(5)
+    src = rng.integers(0, 256, size=(64 << 20) + 12345, dtype=np.uint8)
+    for callers in (1, 2, 5, 8):
+        dst = np.zeros_like(src)
+        threads = L.ndl_debug_parallel_copy(dst.ctypes.data, src.ctypes.data, src.size, callers)
+        assert threads >= 1
+        assert np.array_equal(dst, src), callers
