@@ -54,7 +54,7 @@ DEFAULT_WORKLOAD = "c4b8g"
 # workloads above this many lines are generated as one host block of this size, repeated on the device
 BLOCK_LINES = 1 << 24
 # sizes of the N = 1 `extra` sub-records (ragged / planted generators loop in Python: keep them short)
-EXTRA_LINES = {"c2": 10_000_000, "c3": 4_000_000, "c5": 4_000_000}
+EXTRA_LINES = {"c2": 10_000_000, "c3": 4_000_000, "c5": 10_000_000}  # c5 at 4 M lines is a 0.05 ms launch: launch overhead shows
 
 
 def measured_peak_gbs():

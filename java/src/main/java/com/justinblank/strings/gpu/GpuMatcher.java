@@ -6,6 +6,10 @@ import com.justinblank.strings.Matcher;
  * {@link Matcher} over one string.  Same mutable state as the generated class (nextStart, start, end -
  * DFAClassBuilder.java:688-694), so it is not thread safe either.  Every call is one ndl_match_batch with
  * n = 1; use {@link GpuPattern#matchBatch} for throughput.
+ *
+ * <p>Empty matches: like the reference (DFAClassBuilder.java:634-635), {@code find()} does not move nextStart past an empty
+ * match, so {@code while (m.find())} over a pattern that matches the empty string does not terminate - this class keeps
+ * that behaviour on purpose.  {@link GpuPattern#findAllBatch} reports such a match once and ends the haystack's list.
  */
 final class GpuMatcher implements Matcher {
 

@@ -57,7 +57,11 @@ public final class GpuPattern implements Pattern, AutoCloseable {
         return r;
     }
 
-    /** All non-overlapping matches of every haystack (CSR): {@code while (m.find())} per haystack, in two passes. */
+    /**
+     * All non-overlapping matches of every haystack (CSR): {@code while (m.find())} per haystack, in two passes.
+     * A match that does not move the search position forward (an empty match) is reported once and ends that haystack's list;
+     * the reference's {@code while (m.find())} loop would report it forever.
+     */
     public static final class AllMatches {
         public int[] counts;
         public long[] matchOffsets;
