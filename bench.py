@@ -534,7 +534,7 @@ def measure_long(b, n_total, steps, warmup):
             return sharding.find_long_sharded(
                 lambda entry: pat.find_long_from(data.data_ptr(), n, entry, mem_kind=nb.MEM_DEVICE, stream=stream.cuda_stream),
                 lambda index, entry, li: pat.find_long_back(data.data_ptr(), n, index, entry, li, mem_kind=nb.MEM_DEVICE, stream=stream.cuda_stream),
-                lambda: pat.find_long_from(halo.ctypes.data, halo.size, 0, mem_kind=nb.MEM_HOST, stream=stream.cuda_stream)[1],
+                lambda: pat.walk_host(halo),
                 base, n, rank, world, allgather, fd, bd, pat.reverse_mode, pat.min_length, pat.backwards_root_accepting)
 
     res = None
@@ -569,7 +569,7 @@ def measure_long(b, n_total, steps, warmup):
             return sharding.find_long_sharded(
                 lambda entry: pat.find_long_from(host.data_ptr(), ne, entry, mem_kind=nb.MEM_HOST, stream=stream.cuda_stream),
                 lambda index, entry, li: pat.find_long_back(host.data_ptr(), ne, index, entry, li, mem_kind=nb.MEM_HOST, stream=stream.cuda_stream),
-                lambda: pat.find_long_from(halo.ctypes.data, halo.size, 0, mem_kind=nb.MEM_HOST, stream=stream.cuda_stream)[1],
+                lambda: pat.walk_host(halo),
                 rank * ne, ne, rank, world, allgather, fd, bd, pat.reverse_mode, pat.min_length, pat.backwards_root_accepting)
     step_host()
     b.sync_all()

@@ -7,11 +7,11 @@ state-transition loop over batches of haystacks.  The boundary is the C ABI in i
 from .pattern import (ALL_FLAGS, CASE_INSENSITIVE, DOTALL, LEFTMOST_LONGEST, UNICODE_CASE, UNICODE_CHARACTER_CLASS,
                       DFACompiler, Matcher, NeedleCudaError, Pattern, PatternClassCompilationException, PatternException,
                       PatternSyntaxException, Precompile, compile_to_bytes, encode_haystack, iter_find, pack_haystacks)
-from ._lib import MODE_CONTAINEDIN, MODE_FIND, MODE_MATCHES, MEM_DEVICE, MEM_HOST
+from ._lib import MODE_CONTAINEDIN, MODE_FIND, MODE_MATCHES, MEM_DEVICE, MEM_DEVICE_DATA, MEM_HOST
 
 __all__ = [
     "ALL_FLAGS", "CASE_INSENSITIVE", "DOTALL", "LEFTMOST_LONGEST", "UNICODE_CASE", "UNICODE_CHARACTER_CLASS",
     "DFACompiler", "Matcher", "NeedleCudaError", "Pattern", "PatternClassCompilationException", "PatternException",
     "PatternSyntaxException", "Precompile", "compile_to_bytes", "encode_haystack", "iter_find", "pack_haystacks",
-    "MODE_CONTAINEDIN", "MODE_FIND", "MODE_MATCHES", "MEM_DEVICE", "MEM_HOST",
+    "MODE_CONTAINEDIN", "MODE_FIND", "MODE_MATCHES", "MEM_DEVICE", "MEM_DEVICE_DATA", "MEM_HOST",
 ]

@@ -13,7 +13,7 @@ NDL_OK = 0
 NDL_ESYNTAX, NDL_ECOMPILE, NDL_ETOOLARGE, NDL_EFLAGS = -1, -2, -3, -4
 NDL_ECUDA, NDL_ENCCL, NDL_EINVAL, NDL_EBLOB, NDL_ENOMEM = -5, -6, -7, -8, -9
 MODE_MATCHES, MODE_CONTAINEDIN, MODE_FIND = 0, 1, 2
-MEM_HOST, MEM_DEVICE = 0, 1
+MEM_HOST, MEM_DEVICE, MEM_DEVICE_DATA = 0, 1, 2
 
 
 class BlobInfo(ctypes.Structure):
@@ -32,7 +32,7 @@ SYMBOLS = (
     "ndl_pattern_destroy", "ndl_match_batch", "ndl_find_long", "ndl_last_error", "ndl_version",
     "ndl_device_count", "ndl_kernel_launches", "ndl_pattern_device", "ndl_find_long_from", "ndl_forwards_state_count",
     "ndl_find_long_back", "ndl_backwards_state_count", "ndl_backwards_root_accepting", "ndl_reverse_mode", "ndl_min_length",
-    "ndl_find_all_batch", "ndl_match_lines", "ndl_pattern_device_count", "ndl_host_alloc", "ndl_host_free",
+    "ndl_find_all_batch", "ndl_match_lines", "ndl_pattern_device_count", "ndl_host_alloc", "ndl_host_free", "ndl_forwards_walk_host",
 )
 
 _lib = None
@@ -80,6 +80,8 @@ def lib():
     L.ndl_find_long_back.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
                                      ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
     L.ndl_find_long_back.restype = ctypes.c_int
+    L.ndl_forwards_walk_host.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int32]
+    L.ndl_forwards_walk_host.restype = ctypes.c_int32
     for f in ("ndl_forwards_state_count", "ndl_backwards_state_count", "ndl_backwards_root_accepting", "ndl_reverse_mode", "ndl_min_length"):
         getattr(L, f).argtypes = [ctypes.c_void_p]
         getattr(L, f).restype = ctypes.c_int

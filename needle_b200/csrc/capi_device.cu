@@ -1134,7 +1134,11 @@ static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, in
                           void* stream_, bool host_results = false) {  // host_results: device haystack, results to host pointers
   if (!p) return fail(NDL_EINVAL, "pattern must not be NULL");
   if (char_width != 1 && char_width != 2) return fail(NDL_EINVAL, "char_width must be 1 or 2");
-  if (mem_kind != NDL_MEM_HOST && mem_kind != NDL_MEM_DEVICE) return fail(NDL_EINVAL, "mem_kind must be NDL_MEM_HOST or NDL_MEM_DEVICE");
+  if (mem_kind == NDL_MEM_DEVICE_DATA) {  // device haystack, results to host pointers
+    mem_kind = NDL_MEM_DEVICE;
+    host_results = true;
+  }
+  if (mem_kind != NDL_MEM_HOST && mem_kind != NDL_MEM_DEVICE) return fail(NDL_EINVAL, "mem_kind must be NDL_MEM_HOST, NDL_MEM_DEVICE or NDL_MEM_DEVICE_DATA");
   if (!matched || !end || (!start && !exit_state)) return fail(NDL_EINVAL, "matched, start and end must not be NULL");
   if (from < 0) return fail(NDL_EINVAL, "from must be >= 0");
   if (p->device < 0) return fail(NDL_EINVAL, "ndl_find_long needs a single-device pattern");
@@ -1530,6 +1534,18 @@ int ndl_find_long_from(ndl_pattern* p, const void* data, uint64_t n_chars, int c
                        int64_t last_init, uint8_t* matched, int64_t* start, int64_t* end, int32_t* exit_state, int mem_kind,
                        void* stream) {
   return find_long_impl(p, data, n_chars, char_width, from, entry_state, last_init, matched, start, end, exit_state, mem_kind, stream);
+}
+
+int32_t ndl_forwards_walk_host(const ndl_pattern* p, const void* data, uint64_t n_chars, int char_width, int32_t entry_state) {
+  if (!p || (char_width != 1 && char_width != 2) || (!data && n_chars)) return -1;
+  const HostDeviceTable& t = p->tables[kForwards].host;
+  if (entry_state < 0 || entry_state > t.n_states) return -1;
+  int32_t s = entry_state;
+  for (uint64_t i = 0; i < n_chars; i++) {
+    const uint32_t c = char_width == 1 ? static_cast<const uint8_t*>(data)[i] : static_cast<const uint16_t*>(data)[i];
+    s = t.trans[static_cast<size_t>(s) * t.n_classes + t.cmap[c]];
+  }
+  return s;
 }
 
 int ndl_forwards_state_count(const ndl_pattern* p) { return p ? p->tables[kForwards].host.n_states : -1; }

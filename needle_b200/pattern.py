@@ -256,17 +256,7 @@ class Pattern:
         m = ctypes.c_uint8()
         st, en = ctypes.c_int64(), ctypes.c_int64()
         if mem_kind == _lib.MEM_DEVICE:
-            # results are written through device pointers by the C ABI in that mode; use a small host round trip instead
-            import torch
-            out = getattr(self, "_long_out", None)
-            if out is None:  # one small result buffer per pattern: start, end, matched (low byte of the third word)
-                out = self._long_out = torch.zeros(3, dtype=torch.int64, device=f"cuda:{self.device}")
-            rc = _lib.lib().ndl_find_long(self._h, data_ptr or None, n_chars, char_width, from_, out.data_ptr() + 16, out.data_ptr(),
-                                          out.data_ptr() + 8, mem_kind, stream or None)
-            if rc != _lib.NDL_OK:
-                _raise(rc, "ndl_find_long")
-            o = out.cpu().tolist()
-            return bool(o[2] & 0xFF), int(o[0]), int(o[1])
+            mem_kind = _lib.MEM_DEVICE_DATA  # device haystack, the three scalars through host pointers
         rc = _lib.lib().ndl_find_long(self._h, data_ptr or None, n_chars, char_width, from_, ctypes.byref(m), ctypes.byref(st),
                                       ctypes.byref(en), mem_kind, stream or None)
         if rc != _lib.NDL_OK:
@@ -280,14 +270,7 @@ class Pattern:
         accepting step or -1, `exit_state` = state after the last char read (forwards_state_count = dead)."""
         ex = ctypes.c_int32()
         if mem_kind == _lib.MEM_DEVICE:
-            import torch
-            out = torch.zeros(1, dtype=torch.int64, device=f"cuda:{self.device}")
-            mm = torch.zeros(1, dtype=torch.uint8, device=f"cuda:{self.device}")
-            rc = _lib.lib().ndl_find_long_from(self._h, data_ptr or None, n_chars, char_width, from_, entry_state, -1,
-                                               mm.data_ptr(), None, out.data_ptr(), ctypes.byref(ex), mem_kind, stream or None)
-            if rc != _lib.NDL_OK:
-                _raise(rc, "ndl_find_long_from")
-            return int(out.item()), ex.value
+            mem_kind = _lib.MEM_DEVICE_DATA  # the haystack stays on the device, the three scalars come back through host pointers
         m, en = ctypes.c_uint8(), ctypes.c_int64()
         rc = _lib.lib().ndl_find_long_from(self._h, data_ptr or None, n_chars, char_width, from_, entry_state, -1,
                                            ctypes.byref(m), None, ctypes.byref(en), ctypes.byref(ex), mem_kind, stream or None)
@@ -305,6 +288,16 @@ class Pattern:
         if rc != _lib.NDL_OK:
             _raise(rc, "ndl_find_long_back")
         return st.value, ex.value
+
+    def walk_host(self, data: np.ndarray, entry_state: int = 0, char_width: int = 1) -> int:
+        """The FORWARDS automaton walked on the host over a (short) array from `entry_state`; returns the exit state.  The
+        entry-state guess of a sharded find (ndl_forwards_walk_host): no device work."""
+        data = np.ascontiguousarray(data).view(np.uint8)
+        r = _lib.lib().ndl_forwards_walk_host(self._h, data.ctypes.data if data.size else None, data.size // char_width, char_width,
+                                              entry_state)
+        if r < 0:
+            raise ValueError("ndl_forwards_walk_host: bad argument")
+        return r
 
     @property
     def forwards_state_count(self) -> int:

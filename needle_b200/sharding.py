@@ -151,15 +151,28 @@ def tensor_allgather(device=None):
     dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
                                               if dist.get_backend() == "nccl" else torch.device("cpu"))
 
+    # one small buffer of each kind, reused by every call: pinned host memory on GPUs, so that the two copies are asynchronous DMAs
+    cuda = dev.type == "cuda"
+    mine_h = torch.zeros(5, dtype=torch.int64)
+    out_h = torch.zeros(world * 5, dtype=torch.int64)
+    if cuda:
+        mine_h, out_h = mine_h.pin_memory(), out_h.pin_memory()
+    mine_d = torch.zeros(5, dtype=torch.int64, device=dev) if cuda else mine_h
+    out_d = torch.zeros(world * 5, dtype=torch.int64, device=dev) if cuda else out_h
+    mine_np, out_np = mine_h.numpy(), out_h.numpy()
+
     def allgather(obj):
-        vals = [0, 0, 0, 0, 0]
+        mine_np[:] = 0
         if obj is not None:
-            vals[0] = len(obj)
-            vals[1:1 + len(obj)] = [int(v) for v in obj]
-        mine = torch.tensor(vals, dtype=torch.int64, device=dev)
-        out = torch.empty(world * 5, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(out, mine)
-        rows = out.cpu().view(world, 5).tolist()
+            mine_np[0] = len(obj)
+            mine_np[1:1 + len(obj)] = [int(v) for v in obj]
+        if cuda:
+            mine_d.copy_(mine_h, non_blocking=True)
+        dist.all_gather_into_tensor(out_d, mine_d)
+        if cuda:
+            out_h.copy_(out_d, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+        rows = out_np.reshape(world, 5).tolist()
         return [tuple(r[1:1 + r[0]]) if r[0] else None for r in rows]
     return allgather
 

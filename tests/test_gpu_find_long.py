@@ -154,3 +154,37 @@ def test_device_pointer_entry_and_gigabyte_scale():
     assert pat.find_long_ptrs(data.data_ptr(), n) == (True, n - 9, n)
     data[n - 1] = ord("b")
     assert pat.find_long_ptrs(data.data_ptr(), n) == (False, -1, -1)
+
+
+def test_device_haystack_with_device_or_host_results():
+    """NDL_MEM_DEVICE writes the three results through device pointers, NDL_MEM_DEVICE_DATA through host pointers."""
+    import torch
+    from needle_b200 import _lib
+    pat, ora = pair(workloads.REGEX["c4"])
+    data = ab_buffer(1_000_000, 21)
+    data[777_000], data[777_008] = ord("a"), ord("c")
+    want = oracle_find_long(ora, data)
+    assert want == (True, 777_000, 777_009)
+    d = torch.from_numpy(data).cuda()
+    assert pat.find_long_ptrs(d.data_ptr(), d.numel(), 1, 0, nb.MEM_DEVICE) == want  # (host results under the hood)
+    out = torch.zeros(3, dtype=torch.int64, device="cuda")
+    rc = _lib.lib().ndl_find_long(pat._h, d.data_ptr(), d.numel(), 1, 0, out.data_ptr() + 16, out.data_ptr(), out.data_ptr() + 8,
+                                  _lib.MEM_DEVICE, None)
+    assert rc == _lib.NDL_OK
+    o = out.cpu().tolist()
+    assert (bool(o[2] & 0xFF), o[0], o[1]) == want
+    assert pat.find_long_from(d.data_ptr(), d.numel(), 0, mem_kind=nb.MEM_DEVICE)[0] == 777_009
+
+
+def test_host_walk_gives_the_state_the_device_walk_gives():
+    """ndl_forwards_walk_host (the entry-state guess of a sharded find) against ndl_find_long_from's exit state."""
+    rng = np.random.default_rng(8)
+    for regex in (workloads.REGEX["c4"], r"q[a-z ]*7", workloads.REGEX["c3"], r"Sherlock|Street"):
+        pat, _ = pair(regex)
+        for k in range(20):
+            n = int(rng.integers(0, 40))
+            halo = np.frombuffer(bytes(rng.choice(list(b"abcq7 @.Shtre"), size=n).astype(np.uint8)), dtype=np.uint8).copy() if n else np.zeros(0, np.uint8)
+            entry = int(rng.integers(0, pat.forwards_state_count))
+            host = pat.walk_host(halo, entry)
+            dev = pat.find_long_from(halo.ctypes.data if n else 0, n, entry, mem_kind=nb.MEM_HOST)[1]
+            assert host == dev, (regex, halo.tobytes(), entry)
