@@ -162,7 +162,7 @@ struct ndl_pattern {
   size_t arena_bytes = 0;
   std::mutex ws_mutex;
   Workspace ws;
-  bool long8_ready = false;  // long8_kernel's shared-memory attribute is set
+  bool long8_ready = false, long16_ready = false;  // long8_kernel's shared-memory attribute is set (byte / UTF-16 kernel)
   bool long_refines = false; // the last chunk-parallel find needed refinement passes: the next one records exits from its first pass
   // host-buffer calls are pipelined in chunks: H2D on s_h2d, kernels on the caller's stream, D2H on s_d2h
   static constexpr int kMaxChunks = 16;
@@ -1190,14 +1190,16 @@ static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, in
   r.pos = from;
   if (entry_state < 0 || entry_state > dead) return fail(NDL_EINVAL, "entry_state out of range");
   const bool root_acc = p->tables[kForwards].host.root_accepting;
-  const Lines8Blob& qimg = p->q8[NDL_MODE_FIND];
-  const Lines8Blob& img = qimg.ok && long8_kernel_for(qimg.char_mode) ? qimg : p->l8[NDL_MODE_FIND];
+  const Lines8Blob& qimg = char_width == 1 ? p->q8[NDL_MODE_FIND] : p->q16[NDL_MODE_FIND];
+  const Lines8Blob& img = qimg.ok && long8_kernel_for(qimg.char_mode) ? qimg : char_width == 1 ? p->l8[NDL_MODE_FIND] : p->l16[NDL_MODE_FIND];
+  const int64_t cw = char_width;
   // the chunk-parallel path is for the search phase (no match seen yet) of a pattern with a non-accepting root
-  const bool fast = char_width == 1 && !root_acc && img.ok && long8_kernel_for(img.char_mode) != nullptr && from < n && last_init == -1 &&
-                    entry_state != dead;
+  const bool fast = !root_acc && img.ok && long8_kernel_for(img.char_mode) != nullptr && from < n && last_init == -1 && entry_state != dead &&
+                    (reinterpret_cast<uintptr_t>(d_data) & static_cast<uintptr_t>(cw - 1)) == 0;
 
   if (!fast) {
-    // plain sequential walk (accepting root, UTF-16, no shared-memory image, or continuing a match that is
+    g_long_passes.store(0);  // (test hook: 0 = the chunk-parallel path was not taken)
+    // plain sequential walk (accepting root, no shared-memory image for this char width, or continuing a match that is
     // already under way): DFAClassBuilder.java:335-471
     last = last_init;
     if (root_acc && entry_state == 0 && last_init == -1) last = from < n ? from : 0;
@@ -1218,8 +1220,8 @@ static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, in
       return s1 ? st : st * row_bytes;
     };
     // head: exact walk up to the first 16-byte boundary
-    const uintptr_t a0 = reinterpret_cast<uintptr_t>(d_data) + static_cast<uintptr_t>(from);
-    int64_t head_end = from + static_cast<int64_t>(((a0 + 15) & ~static_cast<uintptr_t>(15)) - a0);
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(d_data) + static_cast<uintptr_t>(from * cw);
+    int64_t head_end = from + static_cast<int64_t>(((a0 + 15) & ~static_cast<uintptr_t>(15)) - a0) / cw;
     if (head_end > n) head_end = n;
     bool done = false;
     if (head_end > from) {
@@ -1236,7 +1238,7 @@ static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, in
       }
     }
     if (!done) {
-      const uint64_t n_segs = static_cast<uint64_t>(n - head_end) / kLongSeg;
+      const uint64_t n_segs = static_cast<uint64_t>(n - head_end) * static_cast<uint64_t>(cw) / kLongSeg;  // segments are 256 BYTES
       const uint64_t n_tiles = (n_segs + 31) / 32;
       int32_t state = r.state;
       int64_t pos = head_end;
@@ -1255,7 +1257,7 @@ static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, in
           ws.seam_cap = cap;
         }
         Long8Params lp;
-        lp.data = d_data + head_end;
+        lp.data = d_data + head_end * cw;
         lp.n_segs = n_segs;
         lp.image = img.dev;
         lp.trans_bytes = img.trans_bytes;
@@ -1263,15 +1265,22 @@ static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, in
         lp.row_bytes = row_bytes;
         lp.entry0 = enc(r.state);
         lp.q = img.q;
+        lp.ua = img.ua;
+        lp.ub = img.ub;
+        lp.xa = img.xa;
+        lp.xb = img.xb;
+        lp.mixed_page = img.mixed_page;
+        lp.replicated = img.replicated;
         lp.seam_guess = ws.seam_guess;
         lp.seam_exit = ws.seam_exit;
         lp.seam_acc = ws.seam_acc;
         lp.first_seg = &d_sc->first_seg;
         lp.first_bad = &d_sc->first_bad;
         Long8Kernel kern = long8_kernel_for(img.char_mode);
-        if (!p->long8_ready) {  // once per pattern (calls are serialised by ws_mutex)
+        bool& ready = char_width == 1 ? p->long8_ready : p->long16_ready;
+        if (!ready) {  // once per pattern and char width (calls are serialised by ws_mutex)
           NDL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kL8DynSmem));
-          p->long8_ready = true;
+          ready = true;
         }
         const uint32_t block_warps = swar ? kQWarps : kL8Warps;
         uint64_t want = (n_tiles + block_warps - 1) / block_warps;
@@ -1292,8 +1301,12 @@ static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, in
           long8_seam_kernel<<<p->sm_count * 4, 256, 0, stream>>>(ws.seam_guess, ws.seam_exit, n_tiles, &d_sc->first_bad);
           g_launches.fetch_add(1);
           NDL_CUDA(cudaGetLastError());
-          long8_epilogue_kernel<<<1, 32, 0, stream>>>(fwd, d_data, head_end, n, n_segs, r.state, dk, ws.seam_exit, ws.seam_acc, &d_sc->first_seg,
-                                                      &d_sc->first_bad, &d_sc->epi);
+          if (char_width == 1)
+            long8_epilogue_kernel<uint8_t><<<1, 32, 0, stream>>>(fwd, d_data, head_end, n, n_segs, r.state, dk, ws.seam_exit, ws.seam_acc,
+                                                                 &d_sc->first_seg, &d_sc->first_bad, &d_sc->epi);
+          else
+            long8_epilogue_kernel<uint16_t><<<1, 32, 0, stream>>>(fwd, reinterpret_cast<const uint16_t*>(d_data), head_end, n, n_segs, r.state, dk,
+                                                                  ws.seam_exit, ws.seam_acc, &d_sc->first_seg, &d_sc->first_bad, &d_sc->epi);
           g_launches.fetch_add(1);
           NDL_CUDA(cudaGetLastError());
           NDL_CUDA(cudaMemcpyAsync(&h.epi, &d_sc->epi, sizeof(Long8Epilogue), cudaMemcpyDeviceToHost, stream));

@@ -2,7 +2,7 @@
 #include "instances.h"
 
 namespace ndl {
-Long8Kernel long8_kernel_for(int cm) {
+Long8Kernel long8_kernel_bytes(int cm) {
   switch (cm) {
     case kCmBytes: return long8_kernel<kCmBytes>;
     case kCmBytes1: return long8_kernel<kCmBytes1>;

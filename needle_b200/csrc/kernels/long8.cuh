@@ -1,4 +1,4 @@
-// long8: find() over ONE long byte haystack (BASELINE config 4: a single 8 GiB string), chunk-parallel.
+// long8: find() over ONE long haystack (BASELINE config 4: a single 8 GiB string; bytes, or UTF-16 code units), chunk-parallel.
 //
 // A DFA walk is sequential, but an unanchored search DFA forgets: while no match has been seen its state
 // is (for most patterns) a function of the last few chars only, because every non-accepting state carries
@@ -106,6 +106,8 @@ struct Long8Params {
   uint32_t root_entry;
   uint32_t row_bytes;      // kCmBytes1 layout
   uint32_t entry0;         // exact entry of segment 0 in the canonical encoding (see canon())
+  uint32_t ua, ub, xa, xb; // UTF-16 class-map modes (kCmHi / kCmMixed), as in Lines8Params
+  int mixed_page, replicated;
   SwarDev q;               // SWAR modes
   uint32_t* seam_guess;    // [n_tiles] lane 0's guessed entry (canonical)
   uint32_t* seam_exit;     // [n_tiles] exit of the tile's last segment (canonical)
@@ -182,7 +184,12 @@ __global__ void __launch_bounds__(cm_is_swar(CM) ? kQThreads : kL8Threads, 1) lo
   L8Ctx cx;
   cx.sel_a = 0x00010000u | (lane * 4);
   cx.sel_b = cx.sel_a | 0x80u;
-  cx.page1 = cx.page3 = cx.ua = cx.ub = cx.xa = cx.xb = 0;
+  cx.page1 = static_cast<uint32_t>(p.mixed_page) << 8;
+  cx.page3 = static_cast<uint32_t>(p.mixed_page) << 24;
+  cx.ua = p.ua;
+  cx.ub = p.ub + (p.replicated == 32 ? lane * 4 : 0);
+  cx.xa = p.xa;
+  cx.xb = p.xb + (p.replicated == 32 ? lane * 4 : 0);
   cx.row_bytes = p.row_bytes;
   cx.root = p.root_entry + lane_off;
   cx.bwd_root = cx.bwd_dead = 0;
@@ -289,10 +296,12 @@ struct Long8Decode {  // canonical table entry -> state id (see long8_kernel)
   uint32_t row_bytes, w_rows, entry_bytes;
 };
 #ifdef NDL_MAIN_TU
-__global__ void long8_epilogue_kernel(DevTable t, const uint8_t* s, int64_t head_end, int64_t n, uint64_t n_segs, int32_t head_state,
+template <typename CharT>
+__global__ void long8_epilogue_kernel(DevTable t, const CharT* s, int64_t head_end, int64_t n, uint64_t n_segs, int32_t head_state,
                                       Long8Decode dec, const uint32_t* seam_exit, const uint32_t* seam_acc, const unsigned long long* first_seg,
                                       const unsigned long long* first_bad, Long8Epilogue* out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  constexpr int64_t kCharBytes = sizeof(CharT);  // positions are in chars, segments in bytes
   const unsigned long long kNone = ~0ull;
   const unsigned long long fs = *first_seg, fb = *first_bad;
   Long8Epilogue o;
@@ -314,14 +323,14 @@ __global__ void long8_epilogue_kernel(DevTable t, const uint8_t* s, int64_t head
   } else if (fs != kNone) {
     // the first accepting segment published the (verified) state at the start of its first accepting 64-byte piece
     const uint32_t acc = seam_acc[fs / 32];
-    const int64_t pos = head_end + static_cast<int64_t>(fs) * kLongSeg + static_cast<int64_t>(acc & 3u) * 64;
-    o.r = dev_seq_walk<uint8_t>(t, s, pos, n, decode(acc >> 2), pos, -1);
+    const int64_t pos = head_end + (static_cast<int64_t>(fs) * kLongSeg + static_cast<int64_t>(acc & 3u) * 64) / kCharBytes;
+    o.r = dev_seq_walk<CharT>(t, s, pos, n, decode(acc >> 2), pos, -1);
   } else {
     const uint64_t n_tiles = (n_segs + 31) / 32;
     const int32_t state = decode(seam_exit[n_tiles - 1]);
-    const int64_t pos = head_end + static_cast<int64_t>(n_segs) * kLongSeg;
+    const int64_t pos = head_end + static_cast<int64_t>(n_segs) * kLongSeg / kCharBytes;
     if (pos < n) {
-      o.r = dev_seq_walk<uint8_t>(t, s, pos, n, state, pos, -1);
+      o.r = dev_seq_walk<CharT>(t, s, pos, n, state, pos, -1);
     } else {
       o.r.pos = pos;
       o.r.state = state;

@@ -188,3 +188,50 @@ def test_host_walk_gives_the_state_the_device_walk_gives():
             host = pat.walk_host(halo, entry)
             dev = pat.find_long_from(halo.ctypes.data if n else 0, n, entry, mem_kind=nb.MEM_HOST)[1]
             assert host == dev, (regex, halo.tobytes(), entry)
+
+
+def test_utf16_haystacks_take_the_chunk_parallel_path():
+    """char_width 2 (a java.lang.String's payload): the same segments / guesses / checks over UTF-16 code units - compares on 16-bit
+    lanes for ASCII patterns, class from the high byte for BMP classes, class-map images otherwise."""
+    from needle_b200 import _lib
+    passes = _lib.lib().ndl_debug_long_passes
+    n = 1_500_000
+    ab = ab_buffer(n + 64, 31).astype(np.uint16)
+    pat, ora = pair(workloads.REGEX["c4"])
+    for shift in (0, 1, 3, 8, 21):  # 2-byte aligned, not 16
+        base = ab[shift:shift + n]
+        assert pat.find_long(base, char_width=2) == oracle_find_long(ora, base, 0, 2) == (False, -1, -1)
+        assert passes() >= 1
+        for pos in (0, 5, 127, 128, 120, 4090, 4096, 1_000_000, n - 9):
+            data = base.copy()
+            data[pos], data[pos + 8] = ord("a"), ord("c")
+            assert pat.find_long(data, char_width=2) == oracle_find_long(ora, data, 0, 2) == (True, pos, pos + 9), (shift, pos)
+        data = base.copy()
+        for pos in (10_000, 900_000):
+            data[pos], data[pos + 8] = ord("a"), ord("c")
+        for frm in (0, 3, 10_001, 899_999, 900_001):
+            assert pat.find_long(data, from_=frm, char_width=2) == oracle_find_long(ora, data, frm, 2), (shift, frm)
+    # chars above 0xff must not alias ASCII ones: 0x0161 / 0x6100 are not 'a'
+    data = ab[:n].copy()
+    data[500_000:500_009] = np.array([0x0161, 0x62, 0x61, 0x62, 0x61, 0x62, 0x62, 0x61, 0x63], dtype=np.uint16)
+    data[700_000:700_009] = np.array([0x61, 0x62, 0x6100, 0x62, 0x61, 0x62, 0x62, 0x61, 0x63], dtype=np.uint16)
+    assert pat.find_long(data, char_width=2) == oracle_find_long(ora, data, 0, 2) == (False, -1, -1)
+
+    # a BMP class (BASELINE config 5's regex) and class-map patterns over UTF-16 text
+    text8, _ = workloads.c3_lines(30_000)
+    text = text8.astype(np.uint16)
+    for regex, plant in ((workloads.REGEX["c5"], [0x0627, 0x0644, 0x0639]), ("Sherlock|Street", [ord(c) for c in "Street"]),
+                         (r"q[a-z ]*7", [ord(c) for c in "q the quick brown fox 7"]), (r"[Ѐ-ӿ]+[0-9]", [0x0416, 0x0417, ord("4")])):
+        pat, ora = pair(regex)
+        data = text.copy()
+        assert pat.find_long(data, char_width=2) == oracle_find_long(ora, data, 0, 2), regex
+        for pos in (1_200_000, 640_000 - 2, 77):
+            d2 = data.copy()
+            d2[pos:pos + len(plant)] = np.array(plant, dtype=np.uint16)
+            for frm in (0, 100, pos + 1):
+                assert pat.find_long(d2, from_=frm, char_width=2) == oracle_find_long(ora, d2, frm, 2), (regex, pos, frm)
+    # which of them ran chunk-parallel is a property of the pattern's UTF-16 images; the two bench regexes must
+    for regex in (workloads.REGEX["c4"], workloads.REGEX["c5"]):
+        pat, ora = pair(regex)
+        pat.find_long(text, char_width=2)
+        assert passes() >= 1, regex
