@@ -31,6 +31,11 @@ for w in want:
 
 rows = list(csv.reader(io.StringIO(run("source"))))
 hdr, data = rows[1], rows[2:]
+# (a report with several launches repeats the header block per launch: keep the first launch's rows)
+for k, r in enumerate(data):
+    if len(r) < len(hdr) or r == hdr:
+        data = data[:k]
+        break
 ia, isrc, ist = hdr.index("Instructions Executed"), hdr.index("Source"), hdr.index("Warp Stall Sampling (All Samples)")
 stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
 tot = sum(int(r[ia]) for r in data)
