@@ -583,3 +583,40 @@ def test_swar_utf16_all_high_bytes():
         chars[::101] = 0xFFFF
         offsets = np.arange(n + 1, dtype=np.uint64) * np.uint64(line_chars)
         assert_batch_equal(workloads.REGEX["c5"], 0, chars.view(np.uint8), offsets, cw=2)
+
+
+def _tiled_on_device(data_b, off_b, reps):
+    """A block of lines repeated `reps` times in device memory (the bytes and an offsets array that keeps counting)."""
+    import torch
+    n_b, block_chars = len(off_b) - 1, int(off_b[-1])
+    data_d = torch.from_numpy(np.ascontiguousarray(data_b).view(np.uint8)).cuda().repeat(reps)
+    off = torch.from_numpy(off_b.astype(np.int64)).cuda()
+    offs = (off[:-1].unsqueeze(0) + (torch.arange(reps, device="cuda", dtype=torch.int64) * block_chars).unsqueeze(1)).reshape(-1)
+    offs = torch.cat([offs, torch.tensor([reps * block_chars], device="cuda", dtype=torch.int64)])
+    return data_d, offs, n_b
+
+
+@pytest.mark.parametrize("key,n_block,reps,cw", [("c3", 1_000_000, 100, 1), ("c5", 500_000, 100, 2)])
+def test_full_size_block_repetition(key, n_block, reps, cw):
+    """BASELINE configs 3 and 5 at their full sizes (100 M ragged lines / 50 M UTF-16 lines): a block of lines the oracle can do
+    in seconds, repeated in device memory.  Every repetition must give the block's results (the blocks sit at different
+    alignments and tile positions), and the first block must equal the oracle."""
+    import torch
+    gen = workloads.c3_lines if key == "c3" else workloads.c5_lines
+    data_b, off_b = gen(n_block)
+    pat, ora = pair(workloads.REGEX[key])
+    data_d, offs, n_b = _tiled_on_device(data_b, off_b, reps)
+    n = n_b * reps
+    m = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    s = torch.zeros(n, dtype=torch.int32, device="cuda")
+    e = torch.zeros(n, dtype=torch.int32, device="cuda")
+    for mode in (2, 1):
+        m.fill_(7), s.fill_(-7), e.fill_(-7)
+        pat.match_batch_ptrs(mode, data_d.data_ptr(), offs.data_ptr(), n, cw, m.data_ptr(), s.data_ptr(), e.data_ptr())
+        torch.cuda.synchronize()
+        em, es, ee = ora.match_batch(mode, data_b, off_b, cw, threads=8)
+        assert np.array_equal(m[:n_b].cpu().numpy(), em)
+        assert bool((m.view(reps, n_b) == m[:n_b]).all())
+        if mode == 2:
+            assert np.array_equal(s[:n_b].cpu().numpy(), es) and np.array_equal(e[:n_b].cpu().numpy(), ee)
+            assert bool((s.view(reps, n_b) == s[:n_b]).all()) and bool((e.view(reps, n_b) == e[:n_b]).all())
