@@ -91,6 +91,15 @@ public final class GpuPattern implements Pattern, AutoCloseable {
     }
 
     /** Convenience: find() on every string. */
+    /**
+     * find() over ONE haystack in a direct buffer (a mapped file, a document) - no per-line structure, 64-bit indices.  On a
+     * pattern compiled for all devices the library cuts the haystack into one chunk per GPU.  Returns {matched (0/1), start, end};
+     * start = end = -1 without a match.
+     */
+    public long[] findLong(ByteBuffer data, long nChars, int charWidth, long from) {
+        return NeedleNative.findLong(handle, data, nChars, charWidth, from);
+    }
+
     public BatchResult findAll(String[] haystacks) {
         return NeedleNative.findAllStrings(handle, haystacks);
     }

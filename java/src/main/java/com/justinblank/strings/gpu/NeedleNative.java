@@ -42,6 +42,9 @@ final class NeedleNative {
     /** Packs the strings with GetStringRegion into one page-locked staging buffer (ndl_host_alloc) and runs find() on all of them. */
     static native GpuPattern.BatchResult findAllStrings(long handle, String[] haystacks);
 
+    /** ndl_find_long with NDL_MEM_HOST on a direct buffer: one haystack, 64-bit indices.  Returns {matched, start, end}. */
+    static native long[] findLong(long handle, ByteBuffer data, long nChars, int charWidth, long from);
+
     /** ndl_host_alloc: a direct ByteBuffer over page-locked memory - batches in it are DMA'd without a bounce copy. */
     static native ByteBuffer pinnedAlloc(long bytes);
 

@@ -162,6 +162,30 @@ JNIEXPORT void JNICALL Java_com_justinblank_strings_gpu_NeedleNative_matchLines(
   if (rc != NDL_OK) throw_for(env, rc);
 }
 
+/* ndl_find_long on a direct buffer: ONE haystack (a memory-mapped file, a document), 64-bit offsets; on a pattern created for all
+ * devices the library splits it across the GPUs.  Returns {matched, start, end}. */
+JNIEXPORT jlongArray JNICALL Java_com_justinblank_strings_gpu_NeedleNative_findLong(JNIEnv* env, jclass k, jlong h, jobject data, jlong nChars,
+                                                                                    jint charWidth, jlong from) {
+  (void)k;
+  if (null_arg(env, data, "data")) return NULL;
+  const void* d = (*env)->GetDirectBufferAddress(env, data);
+  const jlong cap = (*env)->GetDirectBufferCapacity(env, data);
+  if (!d) { throw_named(env, "java/lang/IllegalArgumentException", "data must be a direct buffer"); return NULL; }
+  if (nChars < 0 || (charWidth != 1 && charWidth != 2) || nChars * charWidth > cap) {
+    throw_named(env, "java/lang/IllegalArgumentException", "nChars * charWidth exceeds the buffer");
+    return NULL;
+  }
+  uint8_t matched = 0;
+  int64_t start = -1, end = -1;
+  const int rc = ndl_find_long((ndl_pattern*)(intptr_t)h, d, (uint64_t)nChars, charWidth, (int64_t)from, &matched, &start, &end, NDL_MEM_HOST, NULL);
+  if (rc != NDL_OK) { throw_for(env, rc); return NULL; }
+  jlongArray out = (*env)->NewLongArray(env, 3);
+  if (!out) return NULL;
+  const jlong v[3] = {matched, start, end};
+  (*env)->SetLongArrayRegion(env, out, 0, 3, v);
+  return out;
+}
+
 JNIEXPORT void JNICALL Java_com_justinblank_strings_gpu_NeedleNative_findAllBatch(JNIEnv* env, jclass k, jlong h, jobject data, jobject offsets,
                                                                                   jint n, jint charWidth, jintArray counts,
                                                                                   jobject matchOffsets, jintArray starts, jintArray ends) {

@@ -30,6 +30,7 @@ typedef jobject jthrowable;
 typedef jobject jarray;
 typedef jarray jbyteArray;
 typedef jarray jintArray;
+typedef jarray jlongArray;
 typedef jarray jobjectArray;
 struct _jmethodID;
 typedef struct _jmethodID* jmethodID;
@@ -58,6 +59,8 @@ struct JNINativeInterface_ {
   jobject (*GetObjectArrayElement)(JNIEnv*, jobjectArray, jsize);
   jbyteArray (*NewByteArray)(JNIEnv*, jsize);
   jintArray (*NewIntArray)(JNIEnv*, jsize);
+  jlongArray (*NewLongArray)(JNIEnv*, jsize);
+  void (*SetLongArrayRegion)(JNIEnv*, jlongArray, jsize, jsize, const jlong*);
   void (*GetByteArrayRegion)(JNIEnv*, jbyteArray, jsize, jsize, jbyte*);
   void (*SetByteArrayRegion)(JNIEnv*, jbyteArray, jsize, jsize, const jbyte*);
   void (*GetIntArrayRegion)(JNIEnv*, jintArray, jsize, jsize, jint*);
