@@ -193,3 +193,40 @@ def test_replicas_split_one_long_haystack(three_replicas):
     pat, ora = nb.Pattern(blob, device=-1), Oracle(blob)
     wide[(4 << 20) // 3 - 10], wide[(4 << 20) // 3 + 500] = ord("q"), ord("7")
     assert pat.find_long(wide, char_width=2) == _oracle_find_long(ora, wide, cw=2)
+
+
+def test_concurrent_callers_on_shared_and_separate_patterns():
+    """Host threads calling into the library at once: the same pattern from several threads (calls are serialised on its workspace),
+    different patterns side by side, pageable and pinned buffers mixed (the copy pool serves all of them)."""
+    import threading
+    blob2, blob3 = nb.compile_to_bytes(SSN, 0), nb.compile_to_bytes(workloads.REGEX["c3"], 0)
+    shared, own3 = nb.Pattern(blob2, device=0), nb.Pattern(blob3, device=0)
+    ora2, ora3 = Oracle(blob2), Oracle(blob3)
+    d2, o2 = workloads.c2_lines(400_000)
+    d3, o3 = workloads.c3_lines(300_000)
+    want2 = ora2.match_batch(2, d2, o2, threads=8)
+    want3 = ora3.match_batch(2, d3, o3, threads=8)
+    errors = []
+
+    def worker(k):
+        try:
+            for it in range(4):
+                if k % 2 == 0:
+                    got = shared.match_batch(2, d2, o2)
+                    want = want2
+                else:
+                    pat = own3 if k == 1 else nb.Pattern(blob3, device=0)
+                    got = pat.match_batch(2, d3, o3)
+                    want = want3
+                for g, w in zip(got, want):
+                    if not np.array_equal(g, w):
+                        errors.append((k, it))
+        except Exception as exc:  # noqa: BLE001
+            errors.append((k, repr(exc)))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
