@@ -929,6 +929,10 @@ static int match_multi(ndl_pattern* p, int mode, const void* data, const uint64_
   return NDL_OK;
 }
 
+static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, int char_width, int64_t from, int32_t entry_state,
+                          int64_t last_init, uint8_t* matched, int64_t* start, int64_t* end, int32_t* exit_state, int mem_kind,
+                          void* stream_, bool host_results);
+
 // ndl_match_batch (offsets != NULL) and ndl_match_lines (offsets == NULL: haystack i = data[i * line_chars ..)).
 static int match_impl(ndl_pattern* p, int mode, const void* data, const uint64_t* offsets, uint64_t line_chars, uint64_t n, int char_width,
                       const int32_t* from, uint8_t* matched, int32_t* start, int32_t* end, int mem_kind, void* stream_) {
@@ -966,6 +970,24 @@ static int match_impl(ndl_pattern* p, int mode, const void* data, const uint64_t
     bp.end = end;
     // total chars are only a sizing hint for the fast path; it reads the real offsets on the device
     return launch_batch(p, bp, char_width, 0, stream);
+  }
+  // One long haystack through the batch call (Matcher.find() on a document): a batch kernel would walk it with a single lane.
+  // find() without a `from` is exactly ndl_find_long, which cuts it into segments for the whole GPU.
+  constexpr uint64_t kLongRouteChars = 1u << 16;
+  if (n == 1 && mode == NDL_MODE_FIND && !from) {
+    const uint64_t o0 = offsets ? offsets[0] : 0, o1 = offsets ? offsets[1] : line_chars;
+    if (o1 < o0) return fail(NDL_EINVAL, "offsets must be non-decreasing");
+    if (o1 - o0 >= kLongRouteChars && o1 - o0 < (1ull << 31)) {
+      uint8_t m = 0;
+      int64_t st = -1, en = -1;
+      const int rc = find_long_impl(p, static_cast<const uint8_t*>(data) + o0 * static_cast<uint64_t>(char_width), o1 - o0, char_width, 0, 0, -1, &m,
+                                    &st, &en, nullptr, NDL_MEM_HOST, stream_, false);
+      if (rc != NDL_OK) return rc;
+      matched[0] = m;
+      start[0] = static_cast<int32_t>(st);
+      end[0] = static_cast<int32_t>(en);
+      return NDL_OK;
+    }
   }
   std::lock_guard<std::mutex> lock(p->ws_mutex);
   if (!stream) {  // the replicas of a multi-device pattern run concurrently: each on a stream of its own, not the legacy default stream
@@ -1131,7 +1153,7 @@ struct LongScratch { SeqResult r; unsigned long long first_seg, first_bad; int64
 
 static int find_long_impl(ndl_pattern* p, const void* data, uint64_t n_chars, int char_width, int64_t from, int32_t entry_state,
                           int64_t last_init, uint8_t* matched, int64_t* start, int64_t* end, int32_t* exit_state, int mem_kind,
-                          void* stream_, bool host_results = false) {  // host_results: device haystack, results to host pointers
+                          void* stream_, bool host_results) {  // host_results: device haystack, results to host pointers
   if (!p) return fail(NDL_EINVAL, "pattern must not be NULL");
   if (char_width != 1 && char_width != 2) return fail(NDL_EINVAL, "char_width must be 1 or 2");
   if (mem_kind == NDL_MEM_DEVICE_DATA) {  // device haystack, results to host pointers
@@ -1430,7 +1452,7 @@ static int find_long_multi(ndl_pattern* root, const void* data, uint64_t n_chars
   const int g = static_cast<int>(root->replicas.size());
   constexpr int64_t kMinChunk = 1 << 20;  // below a MiB per GPU the split costs more than it saves
   if (g < 2 || n - from < g * kMinChunk)
-    return find_long_impl(root->replicas[0], data, n_chars, char_width, from, 0, -1, matched, start, end, nullptr, NDL_MEM_HOST, nullptr);
+    return find_long_impl(root->replicas[0], data, n_chars, char_width, from, 0, -1, matched, start, end, nullptr, NDL_MEM_HOST, nullptr, false);
 
   const HostDeviceTable& fwd = root->tables[kForwards].host;
   const int32_t fwd_dead = fwd.n_states, bwd_dead = root->tables[kBackwards].host.n_states;
@@ -1540,13 +1562,13 @@ extern "C" {
 int ndl_find_long(ndl_pattern* p, const void* data, uint64_t n_chars, int char_width, int64_t from, uint8_t* matched,
                   int64_t* start, int64_t* end, int mem_kind, void* stream) {
   if (p && p->device < 0) return find_long_multi(p, data, n_chars, char_width, from, matched, start, end, mem_kind, stream);
-  return find_long_impl(p, data, n_chars, char_width, from, 0, -1, matched, start, end, nullptr, mem_kind, stream);
+  return find_long_impl(p, data, n_chars, char_width, from, 0, -1, matched, start, end, nullptr, mem_kind, stream, false);
 }
 
 int ndl_find_long_from(ndl_pattern* p, const void* data, uint64_t n_chars, int char_width, int64_t from, int32_t entry_state,
                        int64_t last_init, uint8_t* matched, int64_t* start, int64_t* end, int32_t* exit_state, int mem_kind,
                        void* stream) {
-  return find_long_impl(p, data, n_chars, char_width, from, entry_state, last_init, matched, start, end, exit_state, mem_kind, stream);
+  return find_long_impl(p, data, n_chars, char_width, from, entry_state, last_init, matched, start, end, exit_state, mem_kind, stream, false);
 }
 
 int32_t ndl_forwards_walk_host(const ndl_pattern* p, const void* data, uint64_t n_chars, int char_width, int32_t entry_state) {

@@ -230,3 +230,23 @@ def test_concurrent_callers_on_shared_and_separate_patterns():
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_one_long_haystack_through_the_batch_call():
+    """Matcher.find() on a document: a batch of ONE long haystack is routed to the chunk-parallel single-haystack path; same results
+    as the oracle's find(), for byte and UTF-16 haystacks, and the short-haystack / other-mode paths are untouched."""
+    text8, _ = workloads.c3_lines(60_000)  # ~3.8 MB
+    for regex in (workloads.REGEX["c3"], workloads.REGEX["c2"], r"q[a-z ]*7", "Sherlock|Street"):
+        blob = nb.compile_to_bytes(regex, 0)
+        pat, ora = nb.Pattern(blob, device=0), Oracle(blob)
+        for data, cw in ((text8, 1), (text8[:1_500_000].astype(np.uint16).view(np.uint8), 2)):
+            n_chars = data.size // cw
+            for lo, hi in ((0, n_chars), (12_345, n_chars - 7), (0, 65_536), (100, 65_635), (0, 65_535)):
+                off = np.array([lo, hi], dtype=np.uint64)
+                for mode in (2, 1, 0):
+                    got = pat.match_batch(mode, data, off, cw)
+                    want = ora.match_batch(mode, data, off, cw)
+                    for g, w in zip(got, want):
+                        assert g is None or np.array_equal(g, w), (regex, cw, lo, hi, mode)
+    m = nb.DFACompiler.compile(workloads.REGEX["c2"], "Ssn").matcher("x" * 200_000 + "123-45-6789" + "y" * 1000)
+    assert m.find() and (m.start(), m.end()) == (200_000, 200_011)
