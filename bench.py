@@ -436,9 +436,12 @@ def summarise_batch(b, m, peak, peak_src, headline):
                      "kernel": m["kernel"], "kernel_ms": kernel_ms, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": m["in_bytes"],
                      "achieved_with_metadata": (m["in_bytes"] + 17 * m["n"]) / (kernel_ms * 1e-3) / 1e9,
+                     "frac_with_metadata": (m["in_bytes"] + 17 * m["n"]) / (kernel_ms * 1e-3) / 1e9 / peak,
+                     "traffic_gbs": (traffic / (kernel_ms * 1e-3) / 1e9) if traffic else None,
                      "frac_of_nominal_8tbs": achieved / 8000.0,
                      "note": "algorithmic bytes = haystack bytes only (SURVEY.md 8d); achieved_with_metadata adds the 8 B/line of offsets the "
-                             "launch must read and the 9 B/line of results it must write (the API's own traffic, also HBM-bound)"},
+                             "launch must read and the 9 B/line of results it must write (the API's own traffic, also HBM-bound); traffic_gbs = the ncu-measured "
+                             "DRAM bytes per launch (static, see traffic_source) over this run's launch time"},
     }
     if "e2e_ms" in m:
         e2e_value = job_e2e_bytes * m["e2e_steps"] / (e2e_ms * 1e-3) / 1e9
