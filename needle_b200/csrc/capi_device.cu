@@ -312,6 +312,8 @@ static void fill_lines8_params(Lines8Params& lp, const BatchParams& bp, const Li
   lp.char_mode = img.char_mode;
   lp.has_bwd = img.has_bwd ? 1 : 0;
   lp.q = img.q;
+  static const bool no_rounds = std::getenv("NDL_NO_ROUNDS") != nullptr;  // (experiments only)
+  lp.no_rounds = no_rounds ? 1u : 0u;
 }
 
 // Launch the kernels for one batch whose buffers are all on the device.

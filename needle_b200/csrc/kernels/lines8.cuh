@@ -169,6 +169,7 @@ struct Lines8Params {
   int char_mode;
   int has_bwd;  // BACKWARDS pair table resident: table-driven reverse pass runs on the staged tile
   SwarDev q;    // SWAR modes
+  uint32_t no_rounds;  // experiments (NDL_NO_ROUNDS): fixed-length lines keep the resident-tile walks
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1288,9 +1289,279 @@ __device__ __forceinline__ void l8_find_all(const Lines8Params& p, const L8Ctx& 
   cp_async_wait<0>();
 }
 
-// log2cpl: >= 0 fixed-length lines of 16 << log2cpl bytes; kCplAny + cpl: fixed-length lines of 16 * cpl bytes (not a power of
-// two); -1: ragged.
+// ---------------------------------------------------------------------------------------------
+// Fixed-length lines of any multiple of 16 bytes, walked in ROUNDS: a tile is always 32 lines - one per lane - and a round
+// stages the next 64 bytes of each of them (coalesced: four lanes copy one line's 64 bytes; the slots of a 64-byte-line tile)
+// while the previous round is walked.  The resident-tile walks above hold 2048 / L lines per tile, so 96-byte records
+// keep 21 lanes busy, 128-byte records 16 and 256-byte records 8; here every lane is busy for any record length.  The line
+// is not resident when the walk ends, so a table-driven reverse pass reads global memory (l8_finish, resident = false).
+// ---------------------------------------------------------------------------------------------
+template <int CM, bool kOffsets>
+__device__ __forceinline__ void l8_run_rounds(const Lines8Params& p, const L8Ctx& cx, const uint32_t buf0, const uint32_t buf1,
+                                              const uint32_t lane, const uint32_t warp_global, const uint32_t n_warps, const uint32_t cpl) {
+  using CharT = typename std::conditional<L8Chars<CM>::kBytes == 1, uint8_t, uint16_t>::type;
+  constexpr uint32_t kCharBytes = L8Chars<CM>::kBytes;
+  constexpr uint32_t kPer = L8Chars<CM>::kPerChunk;
+  constexpr uint32_t kFlush = 32 / kPer;  // chunks whose accept bits fit in the 32-bit mask (2 or 4: a round is a multiple)
+  const BatchParams& g = p.g;
+  const uint8_t* const data = static_cast<const uint8_t*>(g.data);
+  const uint32_t n = static_cast<uint32_t>(g.n);
+  const uint32_t line_bytes = 16u * cpl, len_chars = line_bytes / kCharBytes;
+  const uint32_t rounds = (cpl + 3) / 4;
+  const uint32_t n_full = n / 32;
+  // this lane's four copies of a round: chunk c = lane + 32 k is part (c & 3) of line (c >> 2)
+  uint32_t dst_off[4], src_off[4];
+#pragma unroll
+  for (uint32_t k = 0; k < 4; k++) {
+    const uint32_t c = lane + 32 * k;
+    dst_off[k] = l8_slot(c >> 2, c & 3, 2) << 4;
+    src_off[k] = (c >> 2) * line_bytes + (c & 3) * 16;
+  }
+  const uint32_t part = lane & 3;  // (the same for the lane's four copies)
+
+  auto load_offsets = [&](uint32_t tile, uint64_t& o0, uint64_t& o1) {
+    const uint32_t i = tile * 32 + lane;
+    if constexpr (kOffsets) {
+      o0 = g.offsets[i];
+      o1 = g.offsets[i + 1];
+    } else {
+      o0 = static_cast<uint64_t>(i) * g.line_chars;
+      o1 = o0 + g.line_chars;
+    }
+  };
+  // are the tile's 32 lines equally spaced and 16-byte aligned?  src: first byte of the tile (the same on every lane if so)
+  auto check = [&](uint64_t o0, uint64_t o1, const uint8_t*& src) -> bool {
+    src = data + (o0 * kCharBytes - static_cast<uint64_t>(lane) * line_bytes);
+    const bool ok = (o1 - o0 == len_chars) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    return __all_sync(0xffffffffu, ok) != 0;
+  };
+  auto stage = [&](const uint8_t* src, uint32_t r, uint32_t buf) {
+    if (4 * r + part < cpl) {
+#pragma unroll
+      for (uint32_t k = 0; k < 4; k++) cp_async16(buf + dst_off[k], src + 64 * r + src_off[k]);
+    }
+    cp_async_commit();
+  };
+
+  uint32_t t = warp_global;
+  uint32_t cur = buf0, nxt = buf1;
+  bool regular = false;
+  const uint8_t* src = data;
+  uint64_t a0 = 0, a1 = 0;  // offsets of the tile after the current one
+  if (t < n_full) {
+    load_offsets(t, a0, a1);
+    regular = check(a0, a1, src);
+    if (regular) stage(src, 0, cur);
+    else cp_async_commit();
+    if (t + n_warps < n_full) load_offsets(t + n_warps, a0, a1);
+  }
+  for (; t < n_full; t += n_warps) {
+    const uint32_t i = t * 32 + lane;
+    uint32_t e = cx.root, mask = 0;
+    int32_t last = g.fwd.root_accepting ? 0 : -1;
+    bool regular_next = false;
+    const uint8_t* src_next = data;
+    for (uint32_t r = 0; r < rounds; r++) {
+      if (r + 1 < rounds) {
+        if (regular) stage(src, r + 1, nxt);
+        else cp_async_commit();
+      } else if (t + n_warps < n_full) {  // the first round of this warp's next tile
+        regular_next = check(a0, a1, src_next);
+        if (regular_next) stage(src_next, 0, nxt);
+        else cp_async_commit();
+        if (t + 2 * n_warps < n_full) load_offsets(t + 2 * n_warps, a0, a1);
+      } else {
+        cp_async_commit();
+      }
+      cp_async_wait<1>();
+      __syncwarp();
+      if (regular) {
+#pragma unroll
+        for (uint32_t cc = 0; cc < 4; cc++) {
+          const uint32_t c = 4 * r + cc;
+          if (c < cpl) {
+            const uint4 w = lds_data16(cur + (l8_slot(lane, cc, 2) << 4));
+            l8_chunk<CM>(w, p.q, cx, e, mask);
+            if ((c % kFlush) == kFlush - 1 || c + 1 == cpl) {  // bit 0 = the most recent char
+              const int32_t cand = static_cast<int32_t>((c + 1) * kPer + 1) - __ffs(mask);
+              last = mask ? cand : last;
+              mask = 0;
+            }
+          }
+        }
+      }
+      __syncwarp();  // every lane is done with `cur` before the stage after next overwrites it
+      const uint32_t tmp = cur;
+      cur = nxt;
+      nxt = tmp;
+    }
+    if (regular) l8_finish<CM, CharT>(p, cx, i, len_chars, last, (e & L8Enc<CM>::kTailFlag) != 0, 0u, [&](uint32_t) { return buf0; }, 0, false);
+    else l8_slow_line<CharT>(g, i);
+    regular = regular_next;
+    src = src_next;
+  }
+  cp_async_wait<0>();
+  // the partial last tile
+  if (warp_global == 0) {
+    const uint32_t i = n_full * 32 + lane;
+    if (i < n) l8_slow_line<CharT>(g, i);
+  }
+}
+
+// The rounds walk for fixed-length lines of ANY byte length (100-byte records ...): the lines of a tile start at different
+// offsets within their 16-byte chunks, so a round copies the aligned chunks that cover the next 64 bytes of every line (addresses
+// by arithmetic - the spacing is known - still four lanes per line), and every lane realigns its own line in registers as the
+// ragged walk does: walk step s needs chunks s and s + 1, so it runs when chunk s + 1 has arrived; the lower chunk is carried.
+template <int CM, bool kOffsets>
+__device__ __forceinline__ void l8_run_rounds_unaligned(const Lines8Params& p, const L8Ctx& cx, const uint32_t buf0, const uint32_t buf1,
+                                                        const uint32_t lane, const uint32_t warp_global, const uint32_t n_warps,
+                                                        const uint32_t line_bytes) {
+  using CharT = typename std::conditional<L8Chars<CM>::kBytes == 1, uint8_t, uint16_t>::type;
+  constexpr uint32_t kCharBytes = L8Chars<CM>::kBytes;
+  constexpr uint32_t kPer = L8Chars<CM>::kPerChunk;
+  const BatchParams& g = p.g;
+  const uint8_t* const data = static_cast<const uint8_t*>(g.data);
+  const uint32_t n = static_cast<uint32_t>(g.n);
+  const uint32_t len_chars = line_bytes / kCharBytes;
+  const uint32_t steps = (len_chars + kPer - 1) / kPer;  // walk steps per line; step s reads chunks s and s + 1 of the line
+  const uint32_t rounds = (steps + 1 + 3) / 4;
+  const uint32_t n_full = n / 32;
+  uint32_t dst_off[4];
+#pragma unroll
+  for (uint32_t k = 0; k < 4; k++) {
+    const uint32_t c = lane + 32 * k;
+    dst_off[k] = l8_slot(c >> 2, c & 3, 2) << 4;
+  }
+  const uint32_t part = lane & 3;
+
+  auto load_offsets = [&](uint32_t tile, uint64_t& o0, uint64_t& o1) {
+    const uint32_t i = tile * 32 + lane;
+    if constexpr (kOffsets) {
+      o0 = g.offsets[i];
+      o1 = g.offsets[i + 1];
+    } else {
+      o0 = static_cast<uint64_t>(i) * g.line_chars;
+      o1 = o0 + g.line_chars;
+    }
+  };
+  // are the tile's 32 lines equally spaced?  base: first byte of the tile's first line (the same on every lane if so)
+  auto check = [&](uint64_t o0, uint64_t o1, const uint8_t*& base) -> bool {
+    base = data + (o0 * kCharBytes - static_cast<uint64_t>(lane) * line_bytes);
+    return __all_sync(0xffffffffu, o1 - o0 == len_chars) != 0;
+  };
+  auto stage = [&](const uint8_t* base, uint32_t r, uint32_t buf) {
+    const uint32_t q = 4 * r + part;  // chunk of the line this lane copies (for four lines)
+#pragma unroll
+    for (uint32_t k = 0; k < 4; k++) {
+      const uint8_t* line = base + ((lane + 32 * k) >> 2) * line_bytes;
+      const uint32_t a = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(line)) & 15u;
+      if (q < ((a + line_bytes + 15u) >> 4)) cp_async16(buf + dst_off[k], line - a + 16 * q);  // (the chunk starts before the line ends)
+    }
+    cp_async_commit();
+  };
+
+  uint32_t t = warp_global;
+  uint32_t cur = buf0, nxt = buf1;
+  bool regular = false;
+  const uint8_t* base = data;
+  uint64_t a0 = 0, a1 = 0;  // offsets of the tile after the current one
+  if (t < n_full) {
+    load_offsets(t, a0, a1);
+    regular = check(a0, a1, base);
+    if (regular) stage(base, 0, cur);
+    else cp_async_commit();
+    if (t + n_warps < n_full) load_offsets(t + n_warps, a0, a1);
+  }
+  for (; t < n_full; t += n_warps) {
+    const uint32_t i = t * 32 + lane;
+    const uint32_t a = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(base + lane * line_bytes)) & 15u;
+    const uint32_t chunks = (a + line_bytes + 15u) >> 4;  // chunks that hold bytes of this lane's line
+    const L8Align al(a);
+    uint32_t e = cx.root, tail_bit = g.fwd.root_accepting ? 1u : 0u;
+    int32_t last = g.fwd.root_accepting ? 0 : -1;
+    uint4 x = make_uint4(0, 0, 0, 0);
+    bool regular_next = false;
+    const uint8_t* base_next = data;
+    for (uint32_t r = 0; r < rounds; r++) {
+      if (r + 1 < rounds) {
+        if (regular) stage(base, r + 1, nxt);
+        else cp_async_commit();
+      } else if (t + n_warps < n_full) {  // the first round of this warp's next tile
+        regular_next = check(a0, a1, base_next);
+        if (regular_next) stage(base_next, 0, nxt);
+        else cp_async_commit();
+        if (t + 2 * n_warps < n_full) load_offsets(t + 2 * n_warps, a0, a1);
+      } else {
+        cp_async_commit();
+      }
+      cp_async_wait<1>();
+      __syncwarp();
+      if (regular) {
+#pragma unroll
+        for (uint32_t cc = 0; cc < 4; cc++) {
+          const uint32_t q = 4 * r + cc;
+          if (q <= steps) {
+            const uint4 y = q < chunks ? lds_data16(cur + (l8_slot(lane, cc, 2) << 4)) : make_uint4(0, 0, 0, 0);
+            if (q > 0) {  // walk step q - 1: chars [(q - 1) kPer, q kPer)
+              uint32_t mask = 0;
+              l8_chunk<CM>(al.apply(x, y), p.q, cx, e, mask);
+              const uint32_t pos = (q - 1) * kPer;
+              const uint32_t valid = min(kPer, len_chars - pos);
+              mask >>= (kPer - valid);  // drop the accept bits of chars past the end of the line
+              const int32_t cand = static_cast<int32_t>(pos + valid + 1) - __ffs(mask);
+              last = mask ? cand : last;
+              tail_bit = mask & 1u;
+            }
+            x = y;
+          }
+        }
+      }
+      __syncwarp();  // every lane is done with `cur` before the stage after next overwrites it
+      const uint32_t tmp = cur;
+      cur = nxt;
+      nxt = tmp;
+    }
+    if (regular) l8_finish<CM, CharT>(p, cx, i, len_chars, last, tail_bit != 0, 0u, [&](uint32_t) { return buf0; }, 0, false);
+    else l8_slow_line<CharT>(g, i);
+    regular = regular_next;
+    base = base_next;
+  }
+  cp_async_wait<0>();
+  if (warp_global == 0) {  // the partial last tile
+    const uint32_t i = n_full * 32 + lane;
+    if (i < n) l8_slow_line<CharT>(g, i);
+  }
+}
+
+// Which walk a batch takes, from the byte length L64 of its first line (every tile re-checks its own lines):
+//   0..4                fixed-length, 16 << k bytes, whole tile resident (l8_run)
+//   kCplAny + cpl       fixed-length, 16 * cpl bytes, whole tile resident with a run-time chunk count (l8_run_any)
+//   kCplRounds + cpl    fixed-length, 16 * cpl bytes, 32 lines per tile walked in rounds of 64 bytes (l8_run_rounds)
+//   kCplRoundsU + L     fixed-length, L bytes (not a multiple of 16), the same with per-line alignment (l8_run_rounds_unaligned)
+//   -1                  ragged
+// Lines of 16, 32, 48 and 64 bytes fill all 32 lanes of a resident tile.  Longer ones do not (2048 / L lines per tile), so they
+// are walked in rounds - measured faster for every pattern kind, also when find() then runs its table-driven reverse pass from
+// global memory instead of the tile (e-mail regex on 256-byte records: 3.75 TB/s against 1.28 with 8 lines per tile).
 constexpr int kCplAny = 100;
+constexpr int kCplRounds = 1000;
+constexpr int kCplRoundsU = 100000;         // + line bytes: fixed-length lines of any byte length, rounds with per-line alignment
+constexpr uint64_t kMinRoundsUnaligned = 17;
+constexpr uint32_t kMaxRoundsCpl = 28;  // up to 448 bytes: beyond, 32 lines at one in-record offset collide in the memory system (measured)
+__device__ __forceinline__ int l8_pick_geometry(const Lines8Params& p, uint64_t L64) {
+  const BatchParams& g = p.g;
+  if (g.from != nullptr && g.mode == 2) return -1;  // find(from, to): the ragged walk takes the per-line start offsets
+  if (L64 >= kMinRoundsUnaligned && L64 <= 16ull * kMaxRoundsCpl && (L64 & 15) != 0 && p.no_rounds == 0) return kCplRoundsU + static_cast<int>(L64);
+  if (L64 < 16 || (L64 & 15) != 0 || (L64 >> 4) > kMaxRoundsCpl) return -1;
+  const uint32_t cpl = static_cast<uint32_t>(L64 >> 4);
+  if (cpl == 1 || cpl == 2 || cpl == 4) return 31 - __clz(cpl);
+  if (cpl == 3) return kCplAny + 3;
+  if (p.no_rounds != 0) {  // (experiments, NDL_NO_ROUNDS: the resident-tile walks of before)
+    if (cpl == 8 || cpl == 16) return 31 - __clz(cpl);
+    return cpl < 8 ? kCplAny + static_cast<int>(cpl) : -1;
+  }
+  return kCplRounds + static_cast<int>(cpl);
+}
+
 template <int CM>
 __device__ __forceinline__ void l8_dispatch(const Lines8Params& p, const L8Ctx& cx, int log2cpl, uint32_t buf0, uint32_t buf1,
                                             uint32_t lane, uint32_t warp_global, uint32_t n_warps) {
@@ -1299,6 +1570,16 @@ __device__ __forceinline__ void l8_dispatch(const Lines8Params& p, const L8Ctx& 
     return;
   }
   const bool off = p.g.offsets != nullptr;
+  if (log2cpl >= kCplRoundsU) {
+    if (off) l8_run_rounds_unaligned<CM, true>(p, cx, buf0, buf1, lane, warp_global, n_warps, static_cast<uint32_t>(log2cpl - kCplRoundsU));
+    else l8_run_rounds_unaligned<CM, false>(p, cx, buf0, buf1, lane, warp_global, n_warps, static_cast<uint32_t>(log2cpl - kCplRoundsU));
+    return;
+  }
+  if (log2cpl >= kCplRounds) {
+    if (off) l8_run_rounds<CM, true>(p, cx, buf0, buf1, lane, warp_global, n_warps, static_cast<uint32_t>(log2cpl - kCplRounds));
+    else l8_run_rounds<CM, false>(p, cx, buf0, buf1, lane, warp_global, n_warps, static_cast<uint32_t>(log2cpl - kCplRounds));
+    return;
+  }
   if (log2cpl >= kCplAny) {
     if (off) l8_run_any<CM, true>(p, cx, buf0, buf1, lane, warp_global, n_warps, static_cast<uint32_t>(log2cpl - kCplAny));
     else l8_run_any<CM, false>(p, cx, buf0, buf1, lane, warp_global, n_warps, static_cast<uint32_t>(log2cpl - kCplAny));
@@ -1368,16 +1649,13 @@ __global__ void __launch_bounds__(kL8Threads, 1) lines8_kernel(const Lines8Param
   const uint32_t char_bytes = (p.char_mode == kCmBytes || p.char_mode == kCmBytes1 || p.char_mode == kCmBytesH) ? 1u : 2u;
   const uint64_t l_chars = batch_off(g, 1) - batch_off(g, 0);
   const uint64_t L64 = l_chars * char_bytes;
-  int log2cpl = -1;
-  if (L64 >= 16 && L64 <= 256 && (L64 & (L64 - 1)) == 0) log2cpl = 31 - __clz(static_cast<uint32_t>(L64)) - 4;
-  else if (L64 > 16 && L64 <= 128 && (L64 & 15) == 0) log2cpl = kCplAny + static_cast<int>(L64 >> 4);  // 48, 80, 96, 112 bytes
+  int log2cpl = l8_pick_geometry(p, L64);
   if (layout_ok) mbar_wait(kL8AbsBar, 0);  // table image has landed
 
   const uint32_t warp_global = blockIdx.x * su.usable_warps + warp;
   const uint32_t n_warps = gridDim.x * su.usable_warps;
   // The fixed-length path is taken when the batch starts with 33 equally spaced offsets of a supported
   // length (its tiles still re-check themselves); everything else goes down the ragged path.
-  if (g.from != nullptr && g.mode == 2) log2cpl = -1;  // find(from, to): the ragged walk takes the per-line start offsets
   if (log2cpl >= 0) {
     const uint32_t probe = static_cast<uint32_t>(min(static_cast<uint64_t>(lane) + 1, g.n - 1));
     const bool same = batch_off(g, probe + 1) - batch_off(g, probe) == l_chars;
@@ -1449,10 +1727,7 @@ __global__ void __launch_bounds__(kQThreads, 1) linesq_kernel(const Lines8Params
   }
   const uint64_t l_chars = batch_off(g, 1) - batch_off(g, 0);
   const uint64_t L64 = l_chars * L8Chars<CM>::kBytes;
-  int log2cpl = -1;
-  if (L64 >= 16 && L64 <= 256 && (L64 & (L64 - 1)) == 0) log2cpl = 31 - __clz(static_cast<uint32_t>(L64)) - 4;
-  else if (L64 > 16 && L64 <= 128 && (L64 & 15) == 0) log2cpl = kCplAny + static_cast<int>(L64 >> 4);  // 48, 80, 96, 112 bytes
-  if (g.from != nullptr && g.mode == 2) log2cpl = -1;  // find(from, to): the ragged walk takes the per-line start offsets
+  int log2cpl = l8_pick_geometry(p, L64);
   if (log2cpl >= 0) {
     const uint32_t probe = static_cast<uint32_t>(min(static_cast<uint64_t>(lane) + 1, g.n - 1));
     const bool same = batch_off(g, probe + 1) - batch_off(g, probe) == l_chars;

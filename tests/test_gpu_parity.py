@@ -135,6 +135,37 @@ def test_fixed_lines_all_lengths(line_len):
     assert_batch_equal(workloads.REGEX["c3"], 0, data[5:], offsets[:4000])
 
 
+@pytest.mark.parametrize("line_len", [80, 96, 112, 128, 160, 256, 272, 512, 1040, 4096, 100, 40, 24, 17, 31, 200, 333, 447])
+def test_fixed_lines_in_rounds(line_len):
+    """Records whose 32-line tile does not fit a buffer are walked in rounds of 64 bytes (every lane busy): fixed-length and
+    variable-length patterns, UTF-16, a batch that is not a multiple of the tile, irregular tiles in between."""
+    rng = np.random.default_rng(line_len)
+    n = 32 * 57 + 19
+    alpha = np.frombuffer(b"0123456789-ab @.", dtype=np.uint8)
+    data = alpha[rng.integers(0, len(alpha), size=n * line_len)]
+    # matches at the very start / end of a record and across round boundaries
+    for i in range(0, n, 7):
+        pos = [0, line_len - 11, 60, 120, 64][i % 5] % (line_len - 10) if line_len > 11 else 0
+        data[i * line_len + pos:i * line_len + pos + 11] = np.frombuffer(b"123-45-6789", dtype=np.uint8)
+    offsets = np.arange(n + 1, dtype=np.uint64) * np.uint64(line_len)
+    for regex in (workloads.REGEX["c2"], workloads.REGEX["c4"], r"[0-9]+", workloads.REGEX["c3"], r"(ab|a|b-)+", "9"):
+        assert_batch_equal(regex, 0, data, offsets)
+    off2 = offsets.copy()
+    off2[1000:] += 16  # one irregular line (tile), the rest regular again
+    assert_batch_equal(workloads.REGEX["c2"], 0, np.concatenate([data, data[:16]]), off2)
+    assert_batch_equal(r"[0-9]+", 0, data[16:], offsets[:n - 1])  # base moved by a whole chunk
+    assert_batch_equal(r"[0-9]+", 0, data[3:], offsets[:n - 1])   # unaligned base: every tile irregular
+    if line_len <= 512:
+        wide = data.astype(np.uint16)
+        o16 = np.arange(n + 1, dtype=np.uint64) * np.uint64(line_len)
+        for regex in (workloads.REGEX["c2"], r"[0-9]+", workloads.REGEX["c5"]):
+            assert_batch_equal(regex, 0, wide.view(np.uint8), o16, cw=2)
+    pat, ora = pair(workloads.REGEX["c2"])
+    m, s_, e = pat.match_lines(2, data, n, line_len)
+    em, es, ee = ora.match_batch(2, data, offsets, 1, threads=4)
+    assert np.array_equal(m, em) and np.array_equal(s_, es) and np.array_equal(e, ee)
+
+
 def test_unaligned_base_and_sub_batches():
     data, offsets = workloads.c2_lines(3000)
     pat, ora = pair(workloads.REGEX["c2"])
