@@ -19,7 +19,7 @@ data = torch.from_numpy(alpha[rng.integers(0, len(alpha), size=total, dtype=np.u
 stream = torch.cuda.current_stream()
 for key in ("c2", "c3"):
     pat = nb.Pattern(nb.compile_to_bytes(workloads.REGEX[key], 0), device=0)
-    for L in (24, 40, 48, 64, 80, 96, 100, 112, 128, 160, 200, 256, 320, 400, 448, 512, 1024):
+    for L in (24, 40, 48, 64, 80, 96, 100, 112, 128, 160, 200, 256, 320, 400, 512, 768, 1024, 2048, 4096, 16384):
         n = total // L
         m = torch.zeros(n, dtype=torch.uint8, device=dev)
         s = torch.zeros(n, dtype=torch.int32, device=dev)

@@ -170,6 +170,7 @@ struct Lines8Params {
   int has_bwd;  // BACKWARDS pair table resident: table-driven reverse pass runs on the staged tile
   SwarDev q;    // SWAR modes
   uint32_t no_rounds;  // experiments (NDL_NO_ROUNDS): fixed-length lines keep the resident-tile walks
+  uint32_t rounds_max_cpl;  // longest record (in 16-byte chunks) walked in rounds: kMaxRoundsCpl (experiments: NDL_ROUNDS_MAX_CPL)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -600,6 +601,11 @@ __device__ __forceinline__ void l8_finish(const Lines8Params& p, const L8Ctx& cx
 // Fixed-length lines: the walk of regular warp tiles, specialised on the line length in BYTES
 // (16 << LOG2CPL) and the char mode.
 // ---------------------------------------------------------------------------------------------
+template <int CM, bool kOffsets>
+__device__ __forceinline__ void l8_run_rounds(const Lines8Params& p, const L8Ctx& cx, const uint32_t buf0, const uint32_t buf1,
+                                              const uint32_t lane, const uint32_t warp_global, const uint32_t n_warps, const uint32_t cpl,
+                                              const uint32_t line_lo);  // (defined below)
+
 template <int LOG2CPL>
 struct L8Geom {
   static constexpr uint32_t kCpl = 1u << LOG2CPL;                                 // 16-byte chunks per line
@@ -709,11 +715,10 @@ __device__ __forceinline__ void l8_run(const Lines8Params& p, const L8Ctx& cx, c
     nxt = tmp;
   }
   cp_async_wait<0>();
-  // the partial last tile
-  if (warp_global == 0) {
-    const uint32_t i = n_full * G::kTileLines + lane;
-    if (i < n) l8_slow_line<CharT>(g, i);
-  }
+  // the partial last tile: the rounds walk takes it (one warp).  A per-thread walk from global memory costs about 0.2 us per
+  // byte of line - 15 us for 64-byte lines, more than a tenth of a 10 M-line launch.
+  if (n_full * G::kTileLines < n)
+    l8_run_rounds<CM, kOffsets>(p, cx, buf0, buf1, lane, warp_global, n_warps, G::kCpl, n_full * G::kTileLines);
 }
 
 // byte offset of 16-byte chunk c of a byte-contiguous tile: the chunk index XOR-swizzled by (chunk >> 3) (ragged tiles, below)
@@ -811,11 +816,8 @@ __device__ __forceinline__ void l8_run_any(const Lines8Params& p, const L8Ctx& c
     nxt = tmp;
   }
   cp_async_wait<0>();
-  // the partial last tile
-  if (warp_global == 0) {
-    const uint32_t i = n_full * tile_lines + lane;
-    if (i < n && lane < tile_lines) l8_slow_line<CharT>(g, i);
-  }
+  // the partial last tile: the rounds walk takes it (one warp)
+  if (n_full * tile_lines < n) l8_run_rounds<CM, kOffsets>(p, cx, buf0, buf1, lane, warp_global, n_warps, cpl, n_full * tile_lines);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1298,7 +1300,9 @@ __device__ __forceinline__ void l8_find_all(const Lines8Params& p, const L8Ctx& 
 // ---------------------------------------------------------------------------------------------
 template <int CM, bool kOffsets>
 __device__ __forceinline__ void l8_run_rounds(const Lines8Params& p, const L8Ctx& cx, const uint32_t buf0, const uint32_t buf1,
-                                              const uint32_t lane, const uint32_t warp_global, const uint32_t n_warps, const uint32_t cpl) {
+                                              const uint32_t lane, const uint32_t warp_global, const uint32_t n_warps, const uint32_t cpl,
+                                              const uint32_t line_lo) {
+  // lines [line_lo, n) in tiles of 32; the last tile may hold fewer lines (its other lanes sit out)
   using CharT = typename std::conditional<L8Chars<CM>::kBytes == 1, uint8_t, uint16_t>::type;
   constexpr uint32_t kCharBytes = L8Chars<CM>::kBytes;
   constexpr uint32_t kPer = L8Chars<CM>::kPerChunk;
@@ -1308,7 +1312,7 @@ __device__ __forceinline__ void l8_run_rounds(const Lines8Params& p, const L8Ctx
   const uint32_t n = static_cast<uint32_t>(g.n);
   const uint32_t line_bytes = 16u * cpl, len_chars = line_bytes / kCharBytes;
   const uint32_t rounds = (cpl + 3) / 4;
-  const uint32_t n_full = n / 32;
+  const uint32_t n_tiles = (n - line_lo + 31) / 32;
   // this lane's four copies of a round: chunk c = lane + 32 k is part (c & 3) of line (c >> 2)
   uint32_t dst_off[4], src_off[4];
 #pragma unroll
@@ -1319,8 +1323,9 @@ __device__ __forceinline__ void l8_run_rounds(const Lines8Params& p, const L8Ctx
   }
   const uint32_t part = lane & 3;  // (the same for the lane's four copies)
 
+  auto lines_in = [&](uint32_t tile) { return min(32u, n - line_lo - tile * 32); };
   auto load_offsets = [&](uint32_t tile, uint64_t& o0, uint64_t& o1) {
-    const uint32_t i = tile * 32 + lane;
+    const uint32_t i = line_lo + tile * 32 + min(lane, lines_in(tile) - 1);  // (lanes without a line repeat the last one)
     if constexpr (kOffsets) {
       o0 = g.offsets[i];
       o1 = g.offsets[i + 1];
@@ -1329,16 +1334,17 @@ __device__ __forceinline__ void l8_run_rounds(const Lines8Params& p, const L8Ctx
       o1 = o0 + g.line_chars;
     }
   };
-  // are the tile's 32 lines equally spaced and 16-byte aligned?  src: first byte of the tile (the same on every lane if so)
-  auto check = [&](uint64_t o0, uint64_t o1, const uint8_t*& src) -> bool {
-    src = data + (o0 * kCharBytes - static_cast<uint64_t>(lane) * line_bytes);
+  // are the tile's lines equally spaced and 16-byte aligned?  src: first byte of the tile (the same on every lane if so)
+  auto check = [&](uint32_t tile, uint64_t o0, uint64_t o1, const uint8_t*& src) -> bool {
+    src = data + (o0 * kCharBytes - static_cast<uint64_t>(min(lane, lines_in(tile) - 1)) * line_bytes);
     const bool ok = (o1 - o0 == len_chars) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
     return __all_sync(0xffffffffu, ok) != 0;
   };
-  auto stage = [&](const uint8_t* src, uint32_t r, uint32_t buf) {
+  auto stage = [&](const uint8_t* src, uint32_t count, uint32_t r, uint32_t buf) {
     if (4 * r + part < cpl) {
 #pragma unroll
-      for (uint32_t k = 0; k < 4; k++) cp_async16(buf + dst_off[k], src + 64 * r + src_off[k]);
+      for (uint32_t k = 0; k < 4; k++)
+        if (((lane + 32 * k) >> 2) < count) cp_async16(buf + dst_off[k], src + 64 * r + src_off[k]);
     }
     cp_async_commit();
   };
@@ -1348,34 +1354,35 @@ __device__ __forceinline__ void l8_run_rounds(const Lines8Params& p, const L8Ctx
   bool regular = false;
   const uint8_t* src = data;
   uint64_t a0 = 0, a1 = 0;  // offsets of the tile after the current one
-  if (t < n_full) {
+  if (t < n_tiles) {
     load_offsets(t, a0, a1);
-    regular = check(a0, a1, src);
-    if (regular) stage(src, 0, cur);
+    regular = check(t, a0, a1, src);
+    if (regular) stage(src, lines_in(t), 0, cur);
     else cp_async_commit();
-    if (t + n_warps < n_full) load_offsets(t + n_warps, a0, a1);
+    if (t + n_warps < n_tiles) load_offsets(t + n_warps, a0, a1);
   }
-  for (; t < n_full; t += n_warps) {
-    const uint32_t i = t * 32 + lane;
+  for (; t < n_tiles; t += n_warps) {
+    const uint32_t count = lines_in(t);
+    const uint32_t i = line_lo + t * 32 + lane;
     uint32_t e = cx.root, mask = 0;
     int32_t last = g.fwd.root_accepting ? 0 : -1;
     bool regular_next = false;
     const uint8_t* src_next = data;
     for (uint32_t r = 0; r < rounds; r++) {
       if (r + 1 < rounds) {
-        if (regular) stage(src, r + 1, nxt);
+        if (regular) stage(src, count, r + 1, nxt);
         else cp_async_commit();
-      } else if (t + n_warps < n_full) {  // the first round of this warp's next tile
-        regular_next = check(a0, a1, src_next);
-        if (regular_next) stage(src_next, 0, nxt);
+      } else if (t + n_warps < n_tiles) {  // the first round of this warp's next tile
+        regular_next = check(t + n_warps, a0, a1, src_next);
+        if (regular_next) stage(src_next, lines_in(t + n_warps), 0, nxt);
         else cp_async_commit();
-        if (t + 2 * n_warps < n_full) load_offsets(t + 2 * n_warps, a0, a1);
+        if (t + 2 * n_warps < n_tiles) load_offsets(t + 2 * n_warps, a0, a1);
       } else {
         cp_async_commit();
       }
       cp_async_wait<1>();
       __syncwarp();
-      if (regular) {
+      if (regular && lane < count) {
 #pragma unroll
         for (uint32_t cc = 0; cc < 4; cc++) {
           const uint32_t c = 4 * r + cc;
@@ -1395,17 +1402,14 @@ __device__ __forceinline__ void l8_run_rounds(const Lines8Params& p, const L8Ctx
       cur = nxt;
       nxt = tmp;
     }
-    if (regular) l8_finish<CM, CharT>(p, cx, i, len_chars, last, (e & L8Enc<CM>::kTailFlag) != 0, 0u, [&](uint32_t) { return buf0; }, 0, false);
-    else l8_slow_line<CharT>(g, i);
+    if (lane < count) {
+      if (regular) l8_finish<CM, CharT>(p, cx, i, len_chars, last, (e & L8Enc<CM>::kTailFlag) != 0, 0u, [&](uint32_t) { return buf0; }, 0, false);
+      else l8_slow_line<CharT>(g, i);
+    }
     regular = regular_next;
     src = src_next;
   }
   cp_async_wait<0>();
-  // the partial last tile
-  if (warp_global == 0) {
-    const uint32_t i = n_full * 32 + lane;
-    if (i < n) l8_slow_line<CharT>(g, i);
-  }
 }
 
 // The rounds walk for fixed-length lines of ANY byte length (100-byte records ...): the lines of a tile start at different
@@ -1425,7 +1429,7 @@ __device__ __forceinline__ void l8_run_rounds_unaligned(const Lines8Params& p, c
   const uint32_t len_chars = line_bytes / kCharBytes;
   const uint32_t steps = (len_chars + kPer - 1) / kPer;  // walk steps per line; step s reads chunks s and s + 1 of the line
   const uint32_t rounds = (steps + 1 + 3) / 4;
-  const uint32_t n_full = n / 32;
+  const uint32_t n_tiles = (n + 31) / 32;  // the last tile may hold fewer lines (its other lanes sit out)
   uint32_t dst_off[4];
 #pragma unroll
   for (uint32_t k = 0; k < 4; k++) {
@@ -1434,8 +1438,9 @@ __device__ __forceinline__ void l8_run_rounds_unaligned(const Lines8Params& p, c
   }
   const uint32_t part = lane & 3;
 
+  auto lines_in = [&](uint32_t tile) { return min(32u, n - tile * 32); };
   auto load_offsets = [&](uint32_t tile, uint64_t& o0, uint64_t& o1) {
-    const uint32_t i = tile * 32 + lane;
+    const uint32_t i = tile * 32 + min(lane, lines_in(tile) - 1);  // (lanes without a line repeat the last one)
     if constexpr (kOffsets) {
       o0 = g.offsets[i];
       o1 = g.offsets[i + 1];
@@ -1444,18 +1449,19 @@ __device__ __forceinline__ void l8_run_rounds_unaligned(const Lines8Params& p, c
       o1 = o0 + g.line_chars;
     }
   };
-  // are the tile's 32 lines equally spaced?  base: first byte of the tile's first line (the same on every lane if so)
-  auto check = [&](uint64_t o0, uint64_t o1, const uint8_t*& base) -> bool {
-    base = data + (o0 * kCharBytes - static_cast<uint64_t>(lane) * line_bytes);
+  // are the tile's lines equally spaced?  base: first byte of the tile's first line (the same on every lane if so)
+  auto check = [&](uint32_t tile, uint64_t o0, uint64_t o1, const uint8_t*& base) -> bool {
+    base = data + (o0 * kCharBytes - static_cast<uint64_t>(min(lane, lines_in(tile) - 1)) * line_bytes);
     return __all_sync(0xffffffffu, o1 - o0 == len_chars) != 0;
   };
-  auto stage = [&](const uint8_t* base, uint32_t r, uint32_t buf) {
+  auto stage = [&](const uint8_t* base, uint32_t count, uint32_t r, uint32_t buf) {
     const uint32_t q = 4 * r + part;  // chunk of the line this lane copies (for four lines)
 #pragma unroll
     for (uint32_t k = 0; k < 4; k++) {
-      const uint8_t* line = base + ((lane + 32 * k) >> 2) * line_bytes;
+      const uint32_t j = (lane + 32 * k) >> 2;
+      const uint8_t* line = base + j * line_bytes;
       const uint32_t a = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(line)) & 15u;
-      if (q < ((a + line_bytes + 15u) >> 4)) cp_async16(buf + dst_off[k], line - a + 16 * q);  // (the chunk starts before the line ends)
+      if (j < count && q < ((a + line_bytes + 15u) >> 4)) cp_async16(buf + dst_off[k], line - a + 16 * q);  // (the chunk starts before the line ends)
     }
     cp_async_commit();
   };
@@ -1465,14 +1471,15 @@ __device__ __forceinline__ void l8_run_rounds_unaligned(const Lines8Params& p, c
   bool regular = false;
   const uint8_t* base = data;
   uint64_t a0 = 0, a1 = 0;  // offsets of the tile after the current one
-  if (t < n_full) {
+  if (t < n_tiles) {
     load_offsets(t, a0, a1);
-    regular = check(a0, a1, base);
-    if (regular) stage(base, 0, cur);
+    regular = check(t, a0, a1, base);
+    if (regular) stage(base, lines_in(t), 0, cur);
     else cp_async_commit();
-    if (t + n_warps < n_full) load_offsets(t + n_warps, a0, a1);
+    if (t + n_warps < n_tiles) load_offsets(t + n_warps, a0, a1);
   }
-  for (; t < n_full; t += n_warps) {
+  for (; t < n_tiles; t += n_warps) {
+    const uint32_t count = lines_in(t);
     const uint32_t i = t * 32 + lane;
     const uint32_t a = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(base + lane * line_bytes)) & 15u;
     const uint32_t chunks = (a + line_bytes + 15u) >> 4;  // chunks that hold bytes of this lane's line
@@ -1484,19 +1491,19 @@ __device__ __forceinline__ void l8_run_rounds_unaligned(const Lines8Params& p, c
     const uint8_t* base_next = data;
     for (uint32_t r = 0; r < rounds; r++) {
       if (r + 1 < rounds) {
-        if (regular) stage(base, r + 1, nxt);
+        if (regular) stage(base, count, r + 1, nxt);
         else cp_async_commit();
-      } else if (t + n_warps < n_full) {  // the first round of this warp's next tile
-        regular_next = check(a0, a1, base_next);
-        if (regular_next) stage(base_next, 0, nxt);
+      } else if (t + n_warps < n_tiles) {  // the first round of this warp's next tile
+        regular_next = check(t + n_warps, a0, a1, base_next);
+        if (regular_next) stage(base_next, lines_in(t + n_warps), 0, nxt);
         else cp_async_commit();
-        if (t + 2 * n_warps < n_full) load_offsets(t + 2 * n_warps, a0, a1);
+        if (t + 2 * n_warps < n_tiles) load_offsets(t + 2 * n_warps, a0, a1);
       } else {
         cp_async_commit();
       }
       cp_async_wait<1>();
       __syncwarp();
-      if (regular) {
+      if (regular && lane < count) {
 #pragma unroll
         for (uint32_t cc = 0; cc < 4; cc++) {
           const uint32_t q = 4 * r + cc;
@@ -1521,16 +1528,14 @@ __device__ __forceinline__ void l8_run_rounds_unaligned(const Lines8Params& p, c
       cur = nxt;
       nxt = tmp;
     }
-    if (regular) l8_finish<CM, CharT>(p, cx, i, len_chars, last, tail_bit != 0, 0u, [&](uint32_t) { return buf0; }, 0, false);
-    else l8_slow_line<CharT>(g, i);
+    if (lane < count) {
+      if (regular) l8_finish<CM, CharT>(p, cx, i, len_chars, last, tail_bit != 0, 0u, [&](uint32_t) { return buf0; }, 0, false);
+      else l8_slow_line<CharT>(g, i);
+    }
     regular = regular_next;
     base = base_next;
   }
   cp_async_wait<0>();
-  if (warp_global == 0) {  // the partial last tile
-    const uint32_t i = n_full * 32 + lane;
-    if (i < n) l8_slow_line<CharT>(g, i);
-  }
 }
 
 // Which walk a batch takes, from the byte length L64 of its first line (every tile re-checks its own lines):
@@ -1546,12 +1551,12 @@ constexpr int kCplAny = 100;
 constexpr int kCplRounds = 1000;
 constexpr int kCplRoundsU = 100000;         // + line bytes: fixed-length lines of any byte length, rounds with per-line alignment
 constexpr uint64_t kMinRoundsUnaligned = 17;
-constexpr uint32_t kMaxRoundsCpl = 28;  // up to 448 bytes: beyond, 32 lines at one in-record offset collide in the memory system (measured)
+constexpr uint32_t kMaxRoundsCpl = 4096;  // records up to 64 KB (longer ones: the ragged walk streams them)
 __device__ __forceinline__ int l8_pick_geometry(const Lines8Params& p, uint64_t L64) {
   const BatchParams& g = p.g;
   if (g.from != nullptr && g.mode == 2) return -1;  // find(from, to): the ragged walk takes the per-line start offsets
-  if (L64 >= kMinRoundsUnaligned && L64 <= 16ull * kMaxRoundsCpl && (L64 & 15) != 0 && p.no_rounds == 0) return kCplRoundsU + static_cast<int>(L64);
-  if (L64 < 16 || (L64 & 15) != 0 || (L64 >> 4) > kMaxRoundsCpl) return -1;
+  if (L64 >= kMinRoundsUnaligned && L64 <= 16ull * p.rounds_max_cpl && (L64 & 15) != 0 && p.no_rounds == 0) return kCplRoundsU + static_cast<int>(L64);
+  if (L64 < 16 || (L64 & 15) != 0 || (L64 >> 4) > p.rounds_max_cpl) return -1;
   const uint32_t cpl = static_cast<uint32_t>(L64 >> 4);
   if (cpl == 1 || cpl == 2 || cpl == 4) return 31 - __clz(cpl);
   if (cpl == 3) return kCplAny + 3;
@@ -1576,8 +1581,8 @@ __device__ __forceinline__ void l8_dispatch(const Lines8Params& p, const L8Ctx& 
     return;
   }
   if (log2cpl >= kCplRounds) {
-    if (off) l8_run_rounds<CM, true>(p, cx, buf0, buf1, lane, warp_global, n_warps, static_cast<uint32_t>(log2cpl - kCplRounds));
-    else l8_run_rounds<CM, false>(p, cx, buf0, buf1, lane, warp_global, n_warps, static_cast<uint32_t>(log2cpl - kCplRounds));
+    if (off) l8_run_rounds<CM, true>(p, cx, buf0, buf1, lane, warp_global, n_warps, static_cast<uint32_t>(log2cpl - kCplRounds), 0u);
+    else l8_run_rounds<CM, false>(p, cx, buf0, buf1, lane, warp_global, n_warps, static_cast<uint32_t>(log2cpl - kCplRounds), 0u);
     return;
   }
   if (log2cpl >= kCplAny) {
