@@ -601,7 +601,7 @@ __device__ __forceinline__ void l8_finish(const Lines8Params& p, const L8Ctx& cx
 // Fixed-length lines: the walk of regular warp tiles, specialised on the line length in BYTES
 // (16 << LOG2CPL) and the char mode.
 // ---------------------------------------------------------------------------------------------
-template <int CM, bool kOffsets>
+template <int CM, bool kOffsets, bool kPartial = false>
 __device__ __forceinline__ void l8_run_rounds(const Lines8Params& p, const L8Ctx& cx, const uint32_t buf0, const uint32_t buf1,
                                               const uint32_t lane, const uint32_t warp_global, const uint32_t n_warps, const uint32_t cpl,
                                               const uint32_t line_lo);  // (defined below)
@@ -718,7 +718,8 @@ __device__ __forceinline__ void l8_run(const Lines8Params& p, const L8Ctx& cx, c
   // the partial last tile: the rounds walk takes it (one warp).  A per-thread walk from global memory costs about 0.2 us per
   // byte of line - 15 us for 64-byte lines, more than a tenth of a 10 M-line launch.
   if (n_full * G::kTileLines < n)
-    l8_run_rounds<CM, kOffsets>(p, cx, buf0, buf1, lane, warp_global, n_warps, G::kCpl, n_full * G::kTileLines);
+    l8_run_rounds<CM, kOffsets, true>(p, cx, buf0, buf1, lane, (warp_global + n_warps - n_full % n_warps) % n_warps, n_warps, G::kCpl,
+                                      n_full * G::kTileLines);
 }
 
 // byte offset of 16-byte chunk c of a byte-contiguous tile: the chunk index XOR-swizzled by (chunk >> 3) (ragged tiles, below)
@@ -817,7 +818,8 @@ __device__ __forceinline__ void l8_run_any(const Lines8Params& p, const L8Ctx& c
   }
   cp_async_wait<0>();
   // the partial last tile: the rounds walk takes it (one warp)
-  if (n_full * tile_lines < n) l8_run_rounds<CM, kOffsets>(p, cx, buf0, buf1, lane, warp_global, n_warps, cpl, n_full * tile_lines);
+  if (n_full * tile_lines < n)
+    l8_run_rounds<CM, kOffsets, true>(p, cx, buf0, buf1, lane, (warp_global + n_warps - n_full % n_warps) % n_warps, n_warps, cpl, n_full * tile_lines);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1298,11 +1300,13 @@ __device__ __forceinline__ void l8_find_all(const Lines8Params& p, const L8Ctx& 
 // keep 21 lanes busy, 128-byte records 16 and 256-byte records 8; here every lane is busy for any record length.  The line
 // is not resident when the walk ends, so a table-driven reverse pass reads global memory (l8_finish, resident = false).
 // ---------------------------------------------------------------------------------------------
-template <int CM, bool kOffsets>
+template <int CM, bool kOffsets, bool kPartial>
 __device__ __forceinline__ void l8_run_rounds(const Lines8Params& p, const L8Ctx& cx, const uint32_t buf0, const uint32_t buf1,
                                               const uint32_t lane, const uint32_t warp_global, const uint32_t n_warps, const uint32_t cpl,
                                               const uint32_t line_lo) {
-  // lines [line_lo, n) in tiles of 32; the last tile may hold fewer lines (its other lanes sit out)
+  // lines [line_lo, n) in tiles of 32.  kPartial = false: the full tiles (then the leftover lines through the kPartial = true
+  // instance, whose tile may hold fewer than 32 lines - its other lanes sit out; kept apart so that the hot loop carries no
+  // per-copy line-count tests)
   using CharT = typename std::conditional<L8Chars<CM>::kBytes == 1, uint8_t, uint16_t>::type;
   constexpr uint32_t kCharBytes = L8Chars<CM>::kBytes;
   constexpr uint32_t kPer = L8Chars<CM>::kPerChunk;
@@ -1312,7 +1316,7 @@ __device__ __forceinline__ void l8_run_rounds(const Lines8Params& p, const L8Ctx
   const uint32_t n = static_cast<uint32_t>(g.n);
   const uint32_t line_bytes = 16u * cpl, len_chars = line_bytes / kCharBytes;
   const uint32_t rounds = (cpl + 3) / 4;
-  const uint32_t n_tiles = (n - line_lo + 31) / 32;
+  const uint32_t n_tiles = kPartial ? (n - line_lo + 31) / 32 : (n - line_lo) / 32;
   // this lane's four copies of a round: chunk c = lane + 32 k is part (c & 3) of line (c >> 2)
   uint32_t dst_off[4], src_off[4];
 #pragma unroll
@@ -1323,7 +1327,7 @@ __device__ __forceinline__ void l8_run_rounds(const Lines8Params& p, const L8Ctx
   }
   const uint32_t part = lane & 3;  // (the same for the lane's four copies)
 
-  auto lines_in = [&](uint32_t tile) { return min(32u, n - line_lo - tile * 32); };
+  auto lines_in = [&](uint32_t tile) { return kPartial ? min(32u, n - line_lo - tile * 32) : 32u; };
   auto load_offsets = [&](uint32_t tile, uint64_t& o0, uint64_t& o1) {
     const uint32_t i = line_lo + tile * 32 + min(lane, lines_in(tile) - 1);  // (lanes without a line repeat the last one)
     if constexpr (kOffsets) {
@@ -1410,16 +1414,22 @@ __device__ __forceinline__ void l8_run_rounds(const Lines8Params& p, const L8Ctx
     src = src_next;
   }
   cp_async_wait<0>();
+  if constexpr (!kPartial) {
+    // the leftover lines go to the warp that is next in the round-robin of tiles (it has one tile fewer than the first warps)
+    if ((n - line_lo) % 32 != 0)
+      l8_run_rounds<CM, kOffsets, true>(p, cx, buf0, buf1, lane, (warp_global + n_warps - n_tiles % n_warps) % n_warps, n_warps, cpl,
+                                        line_lo + n_tiles * 32);
+  }
 }
 
 // The rounds walk for fixed-length lines of ANY byte length (100-byte records ...): the lines of a tile start at different
 // offsets within their 16-byte chunks, so a round copies the aligned chunks that cover the next 64 bytes of every line (addresses
 // by arithmetic - the spacing is known - still four lanes per line), and every lane realigns its own line in registers as the
 // ragged walk does: walk step s needs chunks s and s + 1, so it runs when chunk s + 1 has arrived; the lower chunk is carried.
-template <int CM, bool kOffsets>
+template <int CM, bool kOffsets, bool kPartial = false>
 __device__ __forceinline__ void l8_run_rounds_unaligned(const Lines8Params& p, const L8Ctx& cx, const uint32_t buf0, const uint32_t buf1,
                                                         const uint32_t lane, const uint32_t warp_global, const uint32_t n_warps,
-                                                        const uint32_t line_bytes) {
+                                                        const uint32_t line_bytes, const uint32_t line_lo = 0) {
   using CharT = typename std::conditional<L8Chars<CM>::kBytes == 1, uint8_t, uint16_t>::type;
   constexpr uint32_t kCharBytes = L8Chars<CM>::kBytes;
   constexpr uint32_t kPer = L8Chars<CM>::kPerChunk;
@@ -1429,7 +1439,7 @@ __device__ __forceinline__ void l8_run_rounds_unaligned(const Lines8Params& p, c
   const uint32_t len_chars = line_bytes / kCharBytes;
   const uint32_t steps = (len_chars + kPer - 1) / kPer;  // walk steps per line; step s reads chunks s and s + 1 of the line
   const uint32_t rounds = (steps + 1 + 3) / 4;
-  const uint32_t n_tiles = (n + 31) / 32;  // the last tile may hold fewer lines (its other lanes sit out)
+  const uint32_t n_tiles = kPartial ? (n - line_lo + 31) / 32 : (n - line_lo) / 32;  // (kPartial: as in l8_run_rounds)
   uint32_t dst_off[4];
 #pragma unroll
   for (uint32_t k = 0; k < 4; k++) {
@@ -1438,9 +1448,9 @@ __device__ __forceinline__ void l8_run_rounds_unaligned(const Lines8Params& p, c
   }
   const uint32_t part = lane & 3;
 
-  auto lines_in = [&](uint32_t tile) { return min(32u, n - tile * 32); };
+  auto lines_in = [&](uint32_t tile) { return kPartial ? min(32u, n - line_lo - tile * 32) : 32u; };
   auto load_offsets = [&](uint32_t tile, uint64_t& o0, uint64_t& o1) {
-    const uint32_t i = tile * 32 + min(lane, lines_in(tile) - 1);  // (lanes without a line repeat the last one)
+    const uint32_t i = line_lo + tile * 32 + min(lane, lines_in(tile) - 1);  // (lanes without a line repeat the last one)
     if constexpr (kOffsets) {
       o0 = g.offsets[i];
       o1 = g.offsets[i + 1];
@@ -1480,7 +1490,7 @@ __device__ __forceinline__ void l8_run_rounds_unaligned(const Lines8Params& p, c
   }
   for (; t < n_tiles; t += n_warps) {
     const uint32_t count = lines_in(t);
-    const uint32_t i = t * 32 + lane;
+    const uint32_t i = line_lo + t * 32 + lane;
     const uint32_t a = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(base + lane * line_bytes)) & 15u;
     const uint32_t chunks = (a + line_bytes + 15u) >> 4;  // chunks that hold bytes of this lane's line
     const L8Align al(a);
@@ -1536,6 +1546,11 @@ __device__ __forceinline__ void l8_run_rounds_unaligned(const Lines8Params& p, c
     base = base_next;
   }
   cp_async_wait<0>();
+  if constexpr (!kPartial) {
+    if ((n - line_lo) % 32 != 0)
+      l8_run_rounds_unaligned<CM, kOffsets, true>(p, cx, buf0, buf1, lane, (warp_global + n_warps - n_tiles % n_warps) % n_warps, n_warps, line_bytes,
+                                                  line_lo + n_tiles * 32);
+  }
 }
 
 // Which walk a batch takes, from the byte length L64 of its first line (every tile re-checks its own lines):
