@@ -858,25 +858,28 @@ __device__ __forceinline__ uint32_t warp_sort32(uint32_t key, uint32_t lane) {
 // busy and nothing depends on a line fitting a buffer.  Chunk k of a line is needed as the upper half of walk step
 // k - 1 (the lower half is carried in registers), so a round performs the steps whose upper chunk it holds.
 // The reverse pass of find() reads global memory (the line is not resident).
+// `own`, `line`: whether this lane has a line, and which.  defer_rev (find() with the table-driven reverse pass resident): a
+// line that matched gets matched / end written here and is handed back - return value true, *rev_end / *rev_from - for the
+// caller's reverse queue (ragged_rounds.cuh) instead of running the generic reverse loop over global memory.
 template <int CM, typename CharT>
-__device__ __forceinline__ void l8_stream_group(const Lines8Params& p, const L8Ctx& cx, const uint32_t buf0, const uint32_t buf1,
-                                                const uint32_t lane, const uint32_t c, const uint32_t m, const bool use_from) {
+__device__ __forceinline__ bool l8_stream_lines(const Lines8Params& p, const L8Ctx& cx, const uint32_t buf0, const uint32_t buf1,
+                                                const uint32_t lane, const bool own, const uint32_t line, const bool use_from,
+                                                const bool defer_rev, int32_t* rev_end, int32_t* rev_from) {
   constexpr uint32_t kCharBytes = L8Chars<CM>::kBytes;
   constexpr uint32_t kPer = L8Chars<CM>::kPerChunk;
   const BatchParams& g = p.g;
   const uint8_t* const data = static_cast<const uint8_t*>(g.data);
-  const bool own = lane < m;
   uint64_t o0 = 0;
   uint32_t len = 0;
   int32_t from = 0;
   bool slow = false;
   if (own) {
-    o0 = batch_off(g, c + lane);
-    const uint64_t l64 = batch_off(g, c + lane + 1) - o0;
+    o0 = batch_off(g, line);
+    const uint64_t l64 = batch_off(g, line + 1) - o0;
     slow = l64 >= (1ull << 31);
     len = slow ? 0u : static_cast<uint32_t>(l64);
     if (use_from && !slow) {
-      const int32_t f = g.from[c + lane];
+      const int32_t f = g.from[line];
       if (f < 0 || (f != 0 && static_cast<uint32_t>(f) >= len)) {
         slow = true;  // keeps the reference's corner cases: generic walk
         len = 0;
@@ -947,11 +950,30 @@ __device__ __forceinline__ void l8_stream_group(const Lines8Params& p, const L8C
     nxt = tmp;
   }
   cp_async_wait<0>();
+  bool want_rev = false;
   if (own) {
-    if (slow) l8_slow_line<CharT>(g, c + lane);
-    else l8_finish<CM, CharT>(p, cx, c + lane, len, last, tail_bit != 0, 0u, [&](uint32_t) { return buf0; }, from, false);
+    if (slow) {
+      l8_slow_line<CharT>(g, line);
+    } else if (defer_rev && last != -1) {
+      g.matched[line] = 1;
+      g.end[line] = last + from;
+      *rev_end = last + from;
+      *rev_from = from;
+      want_rev = true;
+    } else {
+      l8_finish<CM, CharT>(p, cx, line, len, last, tail_bit != 0, 0u, [&](uint32_t) { return buf0; }, from, false);
+    }
   }
   __syncwarp();
+  return want_rev;
+}
+
+// 32 consecutive lines starting at c (the long-line path of the ragged tile walk)
+template <int CM, typename CharT>
+__device__ __forceinline__ void l8_stream_group(const Lines8Params& p, const L8Ctx& cx, const uint32_t buf0, const uint32_t buf1,
+                                                const uint32_t lane, const uint32_t c, const uint32_t m, const bool use_from) {
+  int32_t unused_end = 0, unused_from = 0;
+  l8_stream_lines<CM, CharT>(p, cx, buf0, buf1, lane, lane < m, c + lane, use_from, false, &unused_end, &unused_from);
 }
 
 template <int CM>
@@ -1293,6 +1315,10 @@ __device__ __forceinline__ void l8_find_all(const Lines8Params& p, const L8Ctx& 
   cp_async_wait<0>();
 }
 
+}  // namespace ndl
+#include "ragged_rounds.cuh"
+namespace ndl {
+
 // ---------------------------------------------------------------------------------------------
 // Fixed-length lines of any multiple of 16 bytes, walked in ROUNDS: a tile is always 32 lines - one per lane - and a round
 // stages the next 64 bytes of each of them (coalesced: four lanes copy one line's 64 bytes; the slots of a 64-byte-line tile)
@@ -1613,7 +1639,16 @@ __device__ __forceinline__ void l8_dispatch(const Lines8Params& p, const L8Ctx& 
     break;
     NDL_RUN(0) NDL_RUN(1) NDL_RUN(2) NDL_RUN(3) NDL_RUN(4)
 #undef NDL_RUN
-    default: l8_run_ragged<CM>(p, cx, buf0, buf1, lane, warp_global, n_warps); break;
+    default: {
+      // ragged: longer lines (mean length from the first and the last offset) take the sorted streaming walk
+      const uint64_t bytes = (batch_off(p.g, p.g.n) - batch_off(p.g, 0)) * L8Chars<CM>::kBytes;
+      const bool p_from = p.g.from != nullptr && p.g.mode == 2;
+      if (p.g.n >= kRrMinLines && bytes >= static_cast<uint64_t>(kRrMinMeanBytes) * p.g.n && p.no_rounds == 0 && !p_from)
+        l8_run_ragged_rounds<CM>(p, cx, buf0, buf1, lane, warp_global, n_warps);
+      else
+        l8_run_ragged<CM>(p, cx, buf0, buf1, lane, warp_global, n_warps);
+      break;
+    }
   }
 }
 

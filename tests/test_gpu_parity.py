@@ -493,6 +493,46 @@ def test_long_lines_are_streamed(shape):
             assert_batch_equal(regex, 0, wide.view(np.uint8), o16, cw=2)
 
 
+@pytest.mark.parametrize("shape", ["loglike", "u0_400", "u100_300", "mixed_long", "u96_97"])
+def test_ragged_longer_lines_take_the_sorted_streaming_walk(shape):
+    """Ragged batches whose mean line length is 96 bytes or more (log lines): windows of 128 lines sorted by length in registers,
+    batches of 32 similar lines streamed; reverse passes queued.  Against the oracle, all modes, byte and UTF-16 haystacks."""
+    rng = np.random.default_rng(len(shape) + 11)
+    n = 4096 * 3 + 77
+    if shape == "loglike":
+        lens = np.clip(rng.normal(150, 60, size=n), 20, 400).astype(np.int64)
+    elif shape == "u0_400":
+        lens = rng.integers(0, 401, size=n)
+    elif shape == "u100_300":
+        lens = rng.integers(100, 301, size=n)
+    elif shape == "u96_97":
+        lens = rng.integers(96, 98, size=n)
+    else:
+        lens = np.where(rng.random(n) < 0.03, rng.integers(2000, 20000, size=n), rng.integers(30, 260, size=n))
+    offsets = np.zeros(n + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum(lens)
+    total = int(offsets[-1])
+    words = [b"Sherlock", b"Street", b"Holmes and Watson ", b" 123-45-6789 ", b"bob@example.org", b" ", b"x", b"0", b"-", b"\n", b"abababababc",
+             b"the quick brown fox ", b"GET /index.html 200 "]
+    blob = b"".join(words[j] for j in rng.integers(0, len(words), total // 5 + 16))
+    data = np.frombuffer(blob[:total], dtype=np.uint8).copy()
+    sparse = data.copy()
+    sparse[rng.random(total) < 0.97] = ord("q")
+    for regex in (workloads.REGEX["c2"], workloads.REGEX["c3"], workloads.REGEX["c4"], "Sherlock|Street", "[0-9]+x", "q*",
+                  "Holmes.{1,10}Watson|Watson.{1,10}Holmes"):
+        for d in (data, sparse):
+            assert_batch_equal(regex, 0, d, offsets)
+    # a sub-batch that starts in the middle, an unaligned base
+    assert_batch_equal(workloads.REGEX["c3"], 0, data, offsets[1000:9000])
+    assert_batch_equal(workloads.REGEX["c2"], 0, data[3:], (offsets[5:8000] - np.uint64(3)))
+    if shape in ("loglike", "u100_300"):
+        wide = data[:total - total % 2].astype(np.uint16)
+        o16 = offsets.copy()
+        o16[-1] = min(int(o16[-1]), len(wide))
+        for regex in (workloads.REGEX["c2"], workloads.REGEX["c3"], "Sherlock|Street", workloads.REGEX["c5"]):
+            assert_batch_equal(regex, 0, wide.view(np.uint8), o16, cw=2)
+
+
 def fast_path(pat, mode, cw):
     L = _lib.lib()
     L.ndl_debug_fast_path.argtypes = [__import__("ctypes").c_void_p, __import__("ctypes").c_int, __import__("ctypes").c_int]
