@@ -314,6 +314,8 @@ static void fill_lines8_params(Lines8Params& lp, const BatchParams& bp, const Li
   lp.q = img.q;
   static const bool no_rounds = std::getenv("NDL_NO_ROUNDS") != nullptr;  // (experiments only)
   lp.no_rounds = no_rounds ? 1u : 0u;
+  static const char* rr_min = std::getenv("NDL_RR_MIN_MEAN");  // (experiments only)
+  lp.rr_min_mean = rr_min ? static_cast<uint32_t>(std::atoi(rr_min)) : kRrMinMeanBytes;
   static const char* rounds_max = std::getenv("NDL_ROUNDS_MAX_CPL");  // (experiments only)
   lp.rounds_max_cpl = rounds_max ? static_cast<uint32_t>(std::atoi(rounds_max)) : kMaxRoundsCpl;
 }

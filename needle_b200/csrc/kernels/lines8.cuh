@@ -170,6 +170,7 @@ struct Lines8Params {
   int has_bwd;  // BACKWARDS pair table resident: table-driven reverse pass runs on the staged tile
   SwarDev q;    // SWAR modes
   uint32_t no_rounds;  // experiments (NDL_NO_ROUNDS): fixed-length lines keep the resident-tile walks
+  uint32_t rr_min_mean;     // mean line length (bytes) from which ragged batches take the sorted streaming walk: kRrMinMeanBytes (experiments: NDL_RR_MIN_MEAN)
   uint32_t rounds_max_cpl;  // longest record (in 16-byte chunks) walked in rounds: kMaxRoundsCpl (experiments: NDL_ROUNDS_MAX_CPL)
 };
 
@@ -1643,7 +1644,8 @@ __device__ __forceinline__ void l8_dispatch(const Lines8Params& p, const L8Ctx& 
       // ragged: longer lines (mean length from the first and the last offset) take the sorted streaming walk
       const uint64_t bytes = (batch_off(p.g, p.g.n) - batch_off(p.g, 0)) * L8Chars<CM>::kBytes;
       const bool p_from = p.g.from != nullptr && p.g.mode == 2;
-      if (p.g.n >= kRrMinLines && bytes >= static_cast<uint64_t>(kRrMinMeanBytes) * p.g.n && p.no_rounds == 0 && !p_from)
+      // (on shorter lines - mean 64 bytes - it is within +-6 % of the tile walk, depending on the pattern: they keep the tile walk)
+      if (p.g.n >= kRrMinLines && bytes >= static_cast<uint64_t>(p.rr_min_mean) * p.g.n && p.no_rounds == 0 && !p_from)
         l8_run_ragged_rounds<CM>(p, cx, buf0, buf1, lane, warp_global, n_warps);
       else
         l8_run_ragged<CM>(p, cx, buf0, buf1, lane, warp_global, n_warps);
