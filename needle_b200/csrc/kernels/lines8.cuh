@@ -899,11 +899,17 @@ __device__ __forceinline__ bool l8_stream_lines(const Lines8Params& p, const L8C
   const bool aligned = __all_sync(0xffffffffu, a == 0 || iters == 0);
   const uint32_t chunks = iters ? iters + (aligned ? 0u : 1u) : 0;  // chunk k = bytes [ab + 16 k, + 16)
   const uint32_t max_pieces = __reduce_max_sync(0xffffffffu, (chunks + 3) / 4);
+  // chunks to copy: those that start before the end of the line (one 32-bit bound and one pointer per line, set up once)
+  const uint32_t n_copy = static_cast<uint32_t>(min(static_cast<uint64_t>(chunks), (eb - ab + 15) >> 4));
+  const uint8_t* const line_base = data + ab;
+  uint32_t slot_off[4];
+#pragma unroll
+  for (uint32_t cc = 0; cc < 4; cc++) slot_off[cc] = l8_slot(lane, cc, 2) << 4;
   auto stage = [&](uint32_t j, uint32_t buf) {
 #pragma unroll
     for (uint32_t cc = 0; cc < 4; cc++) {
       const uint32_t k = 4 * j + cc;
-      if (k < chunks && ab + 16ull * k < eb) cp_async16(buf + (l8_slot(lane, cc, 2) << 4), data + ab + 16ull * k);
+      if (k < n_copy) cp_async16(buf + slot_off[cc], line_base + 16 * k);
     }
     cp_async_commit();
   };
@@ -933,15 +939,39 @@ __device__ __forceinline__ bool l8_stream_lines(const Lines8Params& p, const L8C
     if (aligned) {
 #pragma unroll
       for (uint32_t cc = 0; cc < 4; cc++)
-        if (4 * j + cc < chunks && pos < len) walk_step(lds_data16(cur + (l8_slot(lane, cc, 2) << 4)));
+        if (4 * j + cc < chunks && pos < len) walk_step(lds_data16(cur + slot_off[cc]));
     } else {
+      // A FULL round: every lane that is still walking has all four chunks of the round and the steps they complete are whole
+      // 16-byte steps - no per-step bounds, no end-of-line masks, one dead-state test for the round (a dead automaton stays dead
+      // and never accepts, so walking on is harmless).  Batches of similar lines (ragged_rounds.cuh) are mostly full rounds.
+      const bool act = pos < len;
+      const bool full = !act || (4 * j + 4 <= chunks && static_cast<uint64_t>(4 * j + 3) * kPer <= len);
+      if (__all_sync(0xffffffffu, full)) {
+        if (act) {
 #pragma unroll
-      for (uint32_t cc = 0; cc < 4; cc++) {
-        const uint32_t k = 4 * j + cc;
-        if (k < chunks) {
-          const uint4 y = lds_data16(cur + (l8_slot(lane, cc, 2) << 4));
-          if (k > 0 && pos < len) walk_step(al.apply(x, y));  // walk step k - 1
-          x = y;
+          for (uint32_t cc = 0; cc < 4; cc++) {
+            const uint4 y = lds_data16(cur + slot_off[cc]);
+            if (j > 0 || cc > 0) {  // walk step 4 j + cc - 1
+              uint32_t mask = 0;
+              l8_chunk<CM>(al.apply(x, y), p.q, cx, e, mask);
+              const int32_t cand = static_cast<int32_t>(pos + kPer + 1) - __ffs(mask);
+              last = mask ? cand : last;
+              tail_bit = mask & 1u;
+              pos += kPer;
+            }
+            x = y;
+          }
+          if ((e & L8Enc<CM>::kStateMask) == cx.fwd_dead) pos = len;
+        }
+      } else {
+#pragma unroll
+        for (uint32_t cc = 0; cc < 4; cc++) {
+          const uint32_t k = 4 * j + cc;
+          if (k < chunks) {
+            const uint4 y = lds_data16(cur + slot_off[cc]);
+            if (k > 0 && pos < len) walk_step(al.apply(x, y));  // walk step k - 1
+            x = y;
+          }
         }
       }
     }
