@@ -2,10 +2,12 @@
 //
 //   lines8_kernel   class map in shared memory (any pattern whose tables fit): pair tables or stride-1 tables
 //   linesq_kernel   packed-compare ("SWAR") classifier, no class map: 4 or 2 chars per transition lookup
-// and what they share: tile staging, the fixed-length walk (l8_run), the ragged walk (l8_run_ragged: two tiles per
-// round, lines paired short + long; long lines streamed, l8_stream_group), the reverse passes on the staged tile
-// (l8_reverse, l8_reverse_char) and the result glue (l8_finish).  long8.cuh builds the single-haystack kernel on the
-// same pieces; layouts.h builds the table images on the host.
+// and what they share: tile staging; the fixed-length walks - resident tiles for records of 16 .. 64 bytes (l8_run, l8_run_any),
+// rounds of 64 bytes per line for every longer record length (l8_run_rounds, l8_run_rounds_unaligned; l8_pick_geometry chooses);
+// the ragged walks - short lines in resident tiles, two per round, lines paired short + long (l8_run_ragged; its long lines
+// streamed, l8_stream_group), longer lines sorted by length and streamed in batches of similar lines (ragged_rounds.cuh); iterated
+// find on the staged tile (l8_find_all); the reverse passes on the staged tile (l8_reverse, l8_reverse_char) and the result glue
+// (l8_finish).  long8.cuh builds the single-haystack kernel on the same pieces; layouts.h builds the table images on the host.
 //
 // Per char the generated Java loop does two dependent array loads (BYTE_CLASSES[c], then
 // STATES[class + state*stride]) plus bookkeeping (DFAClassBuilder.java:438-465).
@@ -38,8 +40,8 @@
 // 32 lines are conflict free too - and double-buffers the next tile against the walk.  Warps never synchronise
 // with each other after the tables have landed.
 //
-// The fixed-length walk needs every line of a warp tile to have the same power-of-two length L in [16, 256] and
-// 16-byte alignment (checked per tile); any other batch takes the ragged walk - same results.
+// The fixed-length walks need every line of a warp tile to have the same length (and, for the aligned ones, 16-byte alignment);
+// this is checked per tile, irregular tiles are walked line by line, and any other batch takes a ragged walk - same results.
 #pragma once
 #include <cuda_runtime.h>
 
