@@ -1634,10 +1634,7 @@ __device__ __forceinline__ int l8_pick_geometry(const Lines8Params& p, uint64_t 
   const uint32_t cpl = static_cast<uint32_t>(L64 >> 4);
   if (cpl == 1 || cpl == 2 || cpl == 4) return 31 - __clz(cpl);
   if (cpl == 3) return kCplAny + 3;
-  if (p.no_rounds != 0) {  // (experiments, NDL_NO_ROUNDS: the resident-tile walks of before)
-    if (cpl == 8 || cpl == 16) return 31 - __clz(cpl);
-    return cpl < 8 ? kCplAny + static_cast<int>(cpl) : -1;
-  }
+  if (p.no_rounds != 0) return cpl < 8 ? kCplAny + static_cast<int>(cpl) : -1;  // (experiments, NDL_NO_ROUNDS: resident tiles / ragged)
   return kCplRounds + static_cast<int>(cpl);
 }
 
@@ -1670,7 +1667,7 @@ __device__ __forceinline__ void l8_dispatch(const Lines8Params& p, const L8Ctx& 
     if (off) l8_run<L, CM, true>(p, cx, buf0, buf1, lane, warp_global, n_warps); \
     else l8_run<L, CM, false>(p, cx, buf0, buf1, lane, warp_global, n_warps);    \
     break;
-    NDL_RUN(0) NDL_RUN(1) NDL_RUN(2) NDL_RUN(3) NDL_RUN(4)
+    NDL_RUN(0) NDL_RUN(1) NDL_RUN(2)  // (128- and 256-byte records: the rounds walk)
 #undef NDL_RUN
     default: {
       // ragged: longer lines (mean length from the first and the last offset) take the sorted streaming walk
