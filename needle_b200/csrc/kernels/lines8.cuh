@@ -577,12 +577,15 @@ __device__ __forceinline__ void l8_finish(const Lines8Params& p, const L8Ctx& cx
     g.matched[i] = m;
   } else if (g.mode == 1) {
     g.matched[i] = last != -1;  // accepting rows of the containedIn automaton are absorbing
+  } else if (g.reverse_mode == 2) {  // start = end - minLength (DFAClassBuilder.java:640-646): no branch on the line's own result
+    const bool hit = last != -1;
+    g.matched[i] = hit;
+    g.start[i] = hit ? last + from - g.min_length : -1;
+    g.end[i] = hit ? last + from : -1;
   } else {
     int32_t st = -1;
     if (last != -1) {
-      if (g.reverse_mode == 2) {  // start = end - minLength (DFAClassBuilder.java:640-646)
-        st = last + from - g.min_length;
-      } else if (g.reverse_mode == 0 && p.has_bwd && resident) {  // indexBackwards (:529-586) on the staged tile
+      if (g.reverse_mode == 0 && p.has_bwd && resident) {  // indexBackwards (:529-586) on the staged tile
         st = have_st ? st_pre : l8_reverse<CM>(p, chunk_addr, ps, last, cx, g.bwd.root_accepting != 0);
         if (st != 0x7fffffff) st += from;
       } else if (g.reverse_mode == 1 && resident) {  // single-char reverse scan (:588-614) on the staged tile
@@ -672,6 +675,7 @@ __device__ __forceinline__ void l8_run(const Lines8Params& p, const L8Ctx& cx, c
   uint32_t cur = buf0, nxt = buf1;
   bool regular = false;
   uint64_t a0 = 0, a1 = 0;  // offsets of the tile after the current one
+  const int32_t last0 = g.fwd.root_accepting ? 0 : -1;
   if (t < n_full) {
     load_offsets(t, a0, a1);
     regular = stage(a0, a1, cur);
@@ -692,7 +696,7 @@ __device__ __forceinline__ void l8_run(const Lines8Params& p, const L8Ctx& cx, c
     if (regular) {
       if (active) {
         uint32_t e = cx.root;
-        int32_t last = g.fwd.root_accepting ? 0 : -1;
+        int32_t last = last0;
         uint32_t mask = 0;
 #pragma unroll
         for (uint32_t c = 0; c < G::kCpl; c++) {
