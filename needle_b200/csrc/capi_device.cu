@@ -977,21 +977,29 @@ static int match_impl(ndl_pattern* p, int mode, const void* data, const uint64_t
     // total chars are only a sizing hint for the fast path; it reads the real offsets on the device
     return launch_batch(p, bp, char_width, 0, stream);
   }
-  // One long haystack through the batch call (Matcher.find() on a document): a batch kernel would walk it with a single lane.
-  // find() without a `from` is exactly ndl_find_long, which cuts it into segments for the whole GPU.
-  constexpr uint64_t kLongRouteChars = 1u << 16;
-  if (n == 1 && mode == NDL_MODE_FIND && !from) {
-    const uint64_t o0 = offsets ? offsets[0] : 0, o1 = offsets ? offsets[1] : line_chars;
-    if (o1 < o0) return fail(NDL_EINVAL, "offsets must be non-decreasing");
-    if (o1 - o0 >= kLongRouteChars && o1 - o0 < (1ull << 31)) {
-      uint8_t m = 0;
-      int64_t st = -1, en = -1;
-      const int rc = find_long_impl(p, static_cast<const uint8_t*>(data) + o0 * static_cast<uint64_t>(char_width), o1 - o0, char_width, 0, 0, -1, &m,
-                                    &st, &en, nullptr, NDL_MEM_HOST, stream_, false);
-      if (rc != NDL_OK) return rc;
-      matched[0] = m;
-      start[0] = static_cast<int32_t>(st);
-      end[0] = static_cast<int32_t>(en);
+  // A few long haystacks through the batch call (Matcher.find() on a document, a handful of files): a batch kernel would walk
+  // each of them with a single lane.  find() without a `from` is exactly ndl_find_long per haystack, which cuts it into segments
+  // for the whole GPU.
+  constexpr uint64_t kLongRouteChars = 1u << 16, kLongRouteMaxLines = 256;
+  if (mode == NDL_MODE_FIND && !from && n <= kLongRouteMaxLines) {
+    bool all_long = true;
+    for (uint64_t i = 0; i < n && all_long; i++) {
+      const uint64_t o0 = offsets ? offsets[i] : i * line_chars, o1 = offsets ? offsets[i + 1] : (i + 1) * line_chars;
+      if (o1 < o0) return fail(NDL_EINVAL, "offsets must be non-decreasing");
+      all_long = o1 - o0 >= kLongRouteChars && o1 - o0 < (1ull << 31);
+    }
+    if (all_long) {
+      for (uint64_t i = 0; i < n; i++) {
+        const uint64_t o0 = offsets ? offsets[i] : i * line_chars, o1 = offsets ? offsets[i + 1] : (i + 1) * line_chars;
+        uint8_t m = 0;
+        int64_t st = -1, en = -1;
+        const int rc = find_long_impl(p, static_cast<const uint8_t*>(data) + o0 * static_cast<uint64_t>(char_width), o1 - o0, char_width, 0, 0, -1, &m,
+                                      &st, &en, nullptr, NDL_MEM_HOST, stream_, false);
+        if (rc != NDL_OK) return rc;
+        matched[i] = m;
+        start[i] = static_cast<int32_t>(st);
+        end[i] = static_cast<int32_t>(en);
+      }
       return NDL_OK;
     }
   }

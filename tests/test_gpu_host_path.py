@@ -248,5 +248,14 @@ def test_one_long_haystack_through_the_batch_call():
                     want = ora.match_batch(mode, data, off, cw)
                     for g, w in zip(got, want):
                         assert g is None or np.array_equal(g, w), (regex, cw, lo, hi, mode)
+    # a handful of long haystacks, and one short one among them (then the batch kernels take the whole batch)
+    blob = nb.compile_to_bytes(workloads.REGEX["c3"], 0)
+    pat, ora = nb.Pattern(blob, device=0), Oracle(blob)
+    for cuts in ([0, 70_000, 1_000_000, 1_070_000, 3_000_000], [0, 70_000, 70_010, 1_500_000], [5, 100_000, 100_000 + 65_536]):
+        off = np.array(cuts, dtype=np.uint64)
+        got = pat.match_batch(2, text8, off, 1)
+        want = ora.match_batch(2, text8, off, 1)
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w), cuts
     m = nb.DFACompiler.compile(workloads.REGEX["c2"], "Ssn").matcher("x" * 200_000 + "123-45-6789" + "y" * 1000)
     assert m.find() and (m.start(), m.end()) == (200_000, 200_011)
