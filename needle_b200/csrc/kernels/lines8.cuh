@@ -1290,6 +1290,9 @@ __device__ __forceinline__ void l8_find_all(const Lines8Params& p, const L8Ctx& 
     const Plan tn = plan_and_stage(cn, nxt);  // (commits a group even when nothing is staged)
     cp_async_wait<1>();
     __syncwarp();
+    // every line of the tile starts on a 16-byte boundary (fixed-length records, mostly): the FIRST search of every line - the
+    // only one for lines without a match - reads its chunks as they are, no realignment
+    const bool tile_aligned = __all_sync(kFull, lane >= t.count || (t.start & 15u) == 0);
     if (lane < t.count) {
       const uint32_t i = c + lane;
       const uint32_t len = t.len;
@@ -1300,25 +1303,41 @@ __device__ __forceinline__ void l8_find_all(const Lines8Params& p, const L8Ctx& 
       }
       auto chunk_addr = [&](uint32_t ch) { return cur + l8_rslot(ch); };
       uint32_t count = 0, from = 0;
+      bool first = tile_aligned;
       for (;;) {
         // indexForwards(from): DFAClassBuilder.java:335-471
         int32_t last = g.fwd.root_accepting ? (from < len ? static_cast<int32_t>(from) : 0) : -1;
         const uint32_t ps = t.start + from * kCharBytes;
-        const L8Align al(ps & 15u);
         uint32_t ch = ps >> 4, pos = from, e = cx.root;
-        uint4 x = lds_data16(chunk_addr(ch));
-        while (pos < len) {
-          const uint4 y = lds_data16(chunk_addr(++ch));
-          const uint4 wv = al.apply(x, y);
-          uint32_t mask = 0;
-          l8_chunk<CM>(wv, p.q, cx, e, mask);
-          const uint32_t valid = min(kPer, len - pos);
-          mask >>= (kPer - valid);  // drop the accept bits of chars past the end of the line
-          const int32_t cand = static_cast<int32_t>(pos + valid + 1) - __ffs(mask);
-          last = mask ? cand : last;
-          x = y;
-          pos += kPer;
-          if ((e & L8Enc<CM>::kStateMask) == cx.fwd_dead) break;
+        if (first) {
+          first = false;
+          while (pos < len) {
+            const uint4 wv = lds_data16(chunk_addr(ch++));
+            uint32_t mask = 0;
+            l8_chunk<CM>(wv, p.q, cx, e, mask);
+            const uint32_t valid = min(kPer, len - pos);
+            mask >>= (kPer - valid);  // drop the accept bits of chars past the end of the line
+            const int32_t cand = static_cast<int32_t>(pos + valid + 1) - __ffs(mask);
+            last = mask ? cand : last;
+            pos += kPer;
+            if ((e & L8Enc<CM>::kStateMask) == cx.fwd_dead) break;
+          }
+        } else {
+          const L8Align al(ps & 15u);
+          uint4 x = lds_data16(chunk_addr(ch));
+          while (pos < len) {
+            const uint4 y = lds_data16(chunk_addr(++ch));
+            const uint4 wv = al.apply(x, y);
+            uint32_t mask = 0;
+            l8_chunk<CM>(wv, p.q, cx, e, mask);
+            const uint32_t valid = min(kPer, len - pos);
+            mask >>= (kPer - valid);  // drop the accept bits of chars past the end of the line
+            const int32_t cand = static_cast<int32_t>(pos + valid + 1) - __ffs(mask);
+            last = mask ? cand : last;
+            x = y;
+            pos += kPer;
+            if ((e & L8Enc<CM>::kStateMask) == cx.fwd_dead) break;
+          }
         }
         if (last == -1) break;
         // start(): DFAClassBuilder.java:640-659, lower bound = from
