@@ -135,12 +135,12 @@ def test_fixed_lines_all_lengths(line_len):
     assert_batch_equal(workloads.REGEX["c3"], 0, data[5:], offsets[:4000])
 
 
-@pytest.mark.parametrize("line_len", [80, 96, 112, 128, 160, 256, 272, 512, 1040, 4096, 100, 40, 24, 17, 31, 200, 333, 447])
+@pytest.mark.parametrize("line_len", [80, 96, 112, 128, 160, 256, 272, 512, 1040, 4096, 100, 40, 24, 17, 31, 200, 333, 447, 16384, 65536, 65552, 5000])
 def test_fixed_lines_in_rounds(line_len):
     """Records whose 32-line tile does not fit a buffer are walked in rounds of 64 bytes (every lane busy): fixed-length and
     variable-length patterns, UTF-16, a batch that is not a multiple of the tile, irregular tiles in between."""
     rng = np.random.default_rng(line_len)
-    n = 32 * 57 + 19
+    n = 32 * 57 + 19 if line_len <= 4096 else 32 * 3 + 5  # (65552 bytes is beyond the rounds walk: the ragged walk streams it)
     alpha = np.frombuffer(b"0123456789-ab @.", dtype=np.uint8)
     data = alpha[rng.integers(0, len(alpha), size=n * line_len)]
     # matches at the very start / end of a record and across round boundaries
@@ -151,7 +151,7 @@ def test_fixed_lines_in_rounds(line_len):
     for regex in (workloads.REGEX["c2"], workloads.REGEX["c4"], r"[0-9]+", workloads.REGEX["c3"], r"(ab|a|b-)+", "9"):
         assert_batch_equal(regex, 0, data, offsets)
     off2 = offsets.copy()
-    off2[1000:] += 16  # one irregular line (tile), the rest regular again
+    off2[min(1000, n // 2):] += 16  # one irregular line (tile), the rest regular again
     assert_batch_equal(workloads.REGEX["c2"], 0, np.concatenate([data, data[:16]]), off2)
     assert_batch_equal(r"[0-9]+", 0, data[16:], offsets[:n - 1])  # base moved by a whole chunk
     assert_batch_equal(r"[0-9]+", 0, data[3:], offsets[:n - 1])   # unaligned base: every tile irregular
