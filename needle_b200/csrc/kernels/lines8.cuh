@@ -911,11 +911,39 @@ __device__ __forceinline__ bool l8_stream_lines(const Lines8Params& p, const L8C
   uint32_t slot_off[4];
 #pragma unroll
   for (uint32_t cc = 0; cc < 4; cc++) slot_off[cc] = l8_slot(lane, cc, 2) << 4;
-  auto stage = [&](uint32_t j, uint32_t buf) {
+  // Group staging: four lanes copy one line's 64 bytes of a round (whole 32-byte sectors per request) instead of every lane
+  // copying 16 bytes of its own line four times (half a sector per request).  Lane l copies chunk (l & 3) of the lines of lanes
+  // (l >> 2) + 8 k; their base (relative to the lowest base of the batch, 32 bits) and copy bound come by shuffle, once per batch.
+  const bool has_copies = n_copy != 0;  // (lanes without a line, empty lines: nothing to copy, no say in the base)
+  uint64_t base_min = has_copies ? reinterpret_cast<uint64_t>(line_base) : ~0ull;
 #pragma unroll
-    for (uint32_t cc = 0; cc < 4; cc++) {
-      const uint32_t k = 4 * j + cc;
-      if (k < n_copy) cp_async16(buf + slot_off[cc], line_base + 16 * k);
+  for (uint32_t d = 16; d > 0; d >>= 1) {
+    const uint64_t other = __shfl_xor_sync(0xffffffffu, base_min, d);
+    base_min = other < base_min ? other : base_min;
+  }
+  const uint64_t rel64 = has_copies ? reinterpret_cast<uint64_t>(line_base) - base_min : 0;
+  const bool grouped = __all_sync(0xffffffffu, rel64 < (1ull << 32));  // (lines of a batch further apart than 4 GiB: own-line staging)
+  uint32_t g_rel[4], g_ncopy[4], g_dst[4];
+#pragma unroll
+  for (uint32_t k = 0; k < 4; k++) {
+    const uint32_t owner = (lane >> 2) + 8 * k;
+    g_rel[k] = __shfl_sync(0xffffffffu, static_cast<uint32_t>(rel64), owner);
+    g_ncopy[k] = __shfl_sync(0xffffffffu, n_copy, owner);
+    g_dst[k] = l8_slot(owner, lane & 3, 2) << 4;
+  }
+  const uint8_t* const group_base = reinterpret_cast<const uint8_t*>(base_min);
+  auto stage = [&](uint32_t j, uint32_t buf) {
+    if (grouped) {
+      const uint32_t q = 4 * j + (lane & 3);
+#pragma unroll
+      for (uint32_t k = 0; k < 4; k++)
+        if (q < g_ncopy[k]) cp_async16(buf + g_dst[k], group_base + g_rel[k] + 16 * q);
+    } else {
+#pragma unroll
+      for (uint32_t cc = 0; cc < 4; cc++) {
+        const uint32_t k = 4 * j + cc;
+        if (k < n_copy) cp_async16(buf + slot_off[cc], line_base + 16 * k);
+      }
     }
     cp_async_commit();
   };
@@ -1435,6 +1463,8 @@ __device__ __forceinline__ void l8_run_rounds(const Lines8Params& p, const L8Ctx
     cp_async_commit();
   };
 
+  const bool defer_rev = g.mode == 2 && g.reverse_mode == 0 && p.has_bwd != 0;  // find() with the table-driven reverse pass
+  L8RevQueue<CM> queue;
   uint32_t t = warp_global;
   uint32_t cur = buf0, nxt = buf1;
   bool regular = false;
@@ -1488,14 +1518,27 @@ __device__ __forceinline__ void l8_run_rounds(const Lines8Params& p, const L8Ctx
       cur = nxt;
       nxt = tmp;
     }
+    bool want_rev = false;
     if (lane < count) {
-      if (regular) l8_finish<CM, CharT>(p, cx, i, len_chars, last, (e & L8Enc<CM>::kTailFlag) != 0, 0u, [&](uint32_t) { return buf0; }, 0, false);
-      else l8_slow_line<CharT>(g, i);
+      if (!regular) {
+        l8_slow_line<CharT>(g, i);
+      } else if (defer_rev && last != -1) {  // the reverse pass of a line that matched: queued, 32 at a time (L8RevQueue)
+        g.matched[i] = 1;
+        g.end[i] = last;
+        want_rev = true;
+      } else {
+        l8_finish<CM, CharT>(p, cx, i, len_chars, last, (e & L8Enc<CM>::kTailFlag) != 0, 0u, [&](uint32_t) { return buf0; }, 0, false);
+      }
+    }
+    if (defer_rev) {
+      const uint32_t rv = __ballot_sync(0xffffffffu, want_rev);
+      if (rv) queue.push(p, cx, lane, rv, i, last, 0);
     }
     regular = regular_next;
     src = src_next;
   }
   cp_async_wait<0>();
+  queue.flush(p, cx, lane);
   if constexpr (!kPartial) {
     // the leftover lines go to the warp that is next in the round-robin of tiles (it has one tile fewer than the first warps)
     if ((n - line_lo) % 32 != 0)
@@ -1558,6 +1601,8 @@ __device__ __forceinline__ void l8_run_rounds_unaligned(const Lines8Params& p, c
     cp_async_commit();
   };
 
+  const bool defer_rev = g.mode == 2 && g.reverse_mode == 0 && p.has_bwd != 0;  // find() with the table-driven reverse pass
+  L8RevQueue<CM> queue;
   uint32_t t = warp_global;
   uint32_t cur = buf0, nxt = buf1;
   bool regular = false;
@@ -1620,14 +1665,27 @@ __device__ __forceinline__ void l8_run_rounds_unaligned(const Lines8Params& p, c
       cur = nxt;
       nxt = tmp;
     }
+    bool want_rev = false;
     if (lane < count) {
-      if (regular) l8_finish<CM, CharT>(p, cx, i, len_chars, last, tail_bit != 0, 0u, [&](uint32_t) { return buf0; }, 0, false);
-      else l8_slow_line<CharT>(g, i);
+      if (!regular) {
+        l8_slow_line<CharT>(g, i);
+      } else if (defer_rev && last != -1) {  // the reverse pass of a line that matched: queued, 32 at a time (L8RevQueue)
+        g.matched[i] = 1;
+        g.end[i] = last;
+        want_rev = true;
+      } else {
+        l8_finish<CM, CharT>(p, cx, i, len_chars, last, tail_bit != 0, 0u, [&](uint32_t) { return buf0; }, 0, false);
+      }
+    }
+    if (defer_rev) {
+      const uint32_t rv = __ballot_sync(0xffffffffu, want_rev);
+      if (rv) queue.push(p, cx, lane, rv, i, last, 0);
     }
     regular = regular_next;
     base = base_next;
   }
   cp_async_wait<0>();
+  queue.flush(p, cx, lane);
   if constexpr (!kPartial) {
     if ((n - line_lo) % 32 != 0)
       l8_run_rounds_unaligned<CM, kOffsets, true>(p, cx, buf0, buf1, lane, (warp_global + n_warps - n_tiles % n_warps) % n_warps, n_warps, line_bytes,

@@ -29,60 +29,24 @@ __device__ __forceinline__ uint4 rr_ldg16(const uint8_t* ptr) {
   return v;
 }
 
-// Ascending bitonic sort of 128 keys, element e = 32 j + lane in key[j].
-__device__ __forceinline__ void rr_sort128(uint32_t (&key)[4], const uint32_t lane) {
-#pragma unroll
-  for (uint32_t k = 2; k <= 128; k <<= 1) {
-#pragma unroll
-    for (uint32_t d = k >> 1; d > 0; d >>= 1) {
-      if (d >= 32) {
-        const uint32_t jd = d >> 5;
-#pragma unroll
-        for (uint32_t j = 0; j < 4; j++) {
-          if ((j & jd) == 0) {
-            const bool up = ((32 * j) & k) == 0;  // (k >= 64 here, so bit k of e is a bit of j)
-            const uint32_t a = key[j], b = key[j | jd];
-            const uint32_t lo = min(a, b), hi = max(a, b);
-            key[j] = up ? lo : hi;
-            key[j | jd] = up ? hi : lo;
-          }
-        }
-      } else {
-#pragma unroll
-        for (uint32_t j = 0; j < 4; j++) {
-          const uint32_t other = __shfl_xor_sync(0xffffffffu, key[j], d);
-          const bool up = ((32 * j + lane) & k) == 0;
-          const bool lower = (lane & d) == 0;
-          key[j] = (lower == up) ? min(key[j], other) : max(key[j], other);
-        }
-      }
-    }
-  }
-}
-
+// The reverse queue: lines that matched and wait for indexBackwards(end - 1, from) (DFAClassBuilder.java:529-586), one per lane.
+// Whenever 32 are waiting they are walked backwards in lockstep straight from global memory / L2 (16-byte loads, one chunk ahead):
+// only lines that matched, so every lane has work - where each lane running the generic loop over its own matches leaves most
+// lanes idle.  Used by the sorted streaming walk below and by the rounds walks of fixed-length records (lines8.cuh): in both the
+// line is no longer in shared memory when its forward walk ends.
 template <int CM>
-__device__ __forceinline__ void l8_run_ragged_rounds(const Lines8Params& p, const L8Ctx& cx, const uint32_t buf0, const uint32_t buf1,
-                                                     const uint32_t lane, const uint32_t warp_global, const uint32_t n_warps) {
-  using CharT = typename std::conditional<L8Chars<CM>::kBytes == 1, uint8_t, uint16_t>::type;
-  constexpr uint32_t kCharBytes = L8Chars<CM>::kBytes;
-  constexpr uint32_t kPer = L8Chars<CM>::kPerChunk;
-  constexpr uint32_t kFull = 0xffffffffu;
-  constexpr uint32_t kStateMask = L8Enc<CM>::kStateMask;
-  const BatchParams& g = p.g;
-  const uint8_t* const data = static_cast<const uint8_t*>(g.data);
-  const uint32_t n = static_cast<uint32_t>(g.n);
-  // windows are dealt out round-robin; smaller windows when there are few lines per warp (long lines), so that every warp has
-  // several and the last ones finish together
-  const uint32_t win = n >= 3u * kRrWindow * n_warps ? kRrWindow : n >= 3u * 64u * n_warps ? 64u : 32u;
-  const uint32_t n_windows = (n + win - 1) / win;
-  const uint32_t mode = static_cast<uint32_t>(g.mode);
-  const bool use_from = g.from != nullptr && mode == 2;
-  const bool defer_rev = mode == 2 && g.reverse_mode == 0 && p.has_bwd != 0;
-
-  // ---- the reverse queue: lane l < qn holds a line that matched and waits for indexBackwards(end - 1, from)
+struct L8RevQueue {
   uint32_t qn = 0, q_line = 0;
   int32_t q_end = 0, q_from = 0;
-  auto reverse_batch = [&](uint32_t count) {  // lockstep over the first `count` entries, straight from global memory / L2
+
+  // lockstep over the first `count` entries
+  __device__ __forceinline__ void run(const Lines8Params& p, const L8Ctx& cx, const uint32_t lane, const uint32_t count) {
+    constexpr uint32_t kCharBytes = L8Chars<CM>::kBytes;
+    constexpr uint32_t kPer = L8Chars<CM>::kPerChunk;
+    constexpr uint32_t kFull = 0xffffffffu;
+    constexpr uint32_t kStateMask = L8Enc<CM>::kStateMask;
+    const BatchParams& g = p.g;
+    const uint8_t* const data = static_cast<const uint8_t*>(g.data);
     const bool has = lane < count;
     uint32_t total = 0;  // chars to walk: [from, end)
     uint64_t o0 = 0;
@@ -121,9 +85,12 @@ __device__ __forceinline__ void l8_run_ragged_rounds(const Lines8Params& p, cons
       x = x_next;
     }
     if (has) g.start[q_line] = w == -1 ? 0x7fffffff : static_cast<int32_t>(total) - w + q_from;
-  };
-  // append the lanes of `rv` (their line / end / from) to the queue; runs a reverse batch whenever 32 entries are waiting
-  auto enqueue = [&](uint32_t rv, uint32_t line, int32_t end, int32_t from) {
+  }
+
+  // append the lanes of `rv` (their line / end / from); runs a batch whenever 32 entries are waiting
+  __device__ __forceinline__ void push(const Lines8Params& p, const L8Ctx& cx, const uint32_t lane, const uint32_t rv, const uint32_t line,
+                                       const int32_t end, const int32_t from) {
+    constexpr uint32_t kFull = 0xffffffffu;
     const uint32_t k = __popc(rv);
     {  // slot s of the queue takes the (s - qn)-th lane of rv
       const bool mine = lane >= qn && lane < qn + k;
@@ -133,7 +100,7 @@ __device__ __forceinline__ void l8_run_ragged_rounds(const Lines8Params& p, cons
       if (mine) { q_line = nl; q_end = ne; q_from = nf; }
     }
     if (qn + k >= 32) {
-      reverse_batch(32);
+      run(p, cx, lane, 32);
       const uint32_t done = 32 - qn, rest = k - done;  // `done` lanes of rv went into the batch; the rest start a new queue
       const bool mine = lane < rest;
       const uint32_t src = mine ? __fns(rv, 0, static_cast<int>(done + lane) + 1) & 31u : lane;
@@ -144,7 +111,62 @@ __device__ __forceinline__ void l8_run_ragged_rounds(const Lines8Params& p, cons
     } else {
       qn += k;
     }
-  };
+  }
+
+  __device__ __forceinline__ void flush(const Lines8Params& p, const L8Ctx& cx, const uint32_t lane) {
+    if (qn) run(p, cx, lane, qn);
+    qn = 0;
+  }
+};
+
+// Ascending bitonic sort of 128 keys, element e = 32 j + lane in key[j].
+__device__ __forceinline__ void rr_sort128(uint32_t (&key)[4], const uint32_t lane) {
+#pragma unroll
+  for (uint32_t k = 2; k <= 128; k <<= 1) {
+#pragma unroll
+    for (uint32_t d = k >> 1; d > 0; d >>= 1) {
+      if (d >= 32) {
+        const uint32_t jd = d >> 5;
+#pragma unroll
+        for (uint32_t j = 0; j < 4; j++) {
+          if ((j & jd) == 0) {
+            const bool up = ((32 * j) & k) == 0;  // (k >= 64 here, so bit k of e is a bit of j)
+            const uint32_t a = key[j], b = key[j | jd];
+            const uint32_t lo = min(a, b), hi = max(a, b);
+            key[j] = up ? lo : hi;
+            key[j | jd] = up ? hi : lo;
+          }
+        }
+      } else {
+#pragma unroll
+        for (uint32_t j = 0; j < 4; j++) {
+          const uint32_t other = __shfl_xor_sync(0xffffffffu, key[j], d);
+          const bool up = ((32 * j + lane) & k) == 0;
+          const bool lower = (lane & d) == 0;
+          key[j] = (lower == up) ? min(key[j], other) : max(key[j], other);
+        }
+      }
+    }
+  }
+}
+
+template <int CM>
+__device__ __forceinline__ void l8_run_ragged_rounds(const Lines8Params& p, const L8Ctx& cx, const uint32_t buf0, const uint32_t buf1,
+                                                     const uint32_t lane, const uint32_t warp_global, const uint32_t n_warps) {
+  using CharT = typename std::conditional<L8Chars<CM>::kBytes == 1, uint8_t, uint16_t>::type;
+  constexpr uint32_t kCharBytes = L8Chars<CM>::kBytes;
+  constexpr uint32_t kFull = 0xffffffffu;
+  const BatchParams& g = p.g;
+  const uint32_t n = static_cast<uint32_t>(g.n);
+  // windows are dealt out round-robin; smaller windows when there are few lines per warp (long lines), so that every warp has
+  // several and the last ones finish together
+  const uint32_t win = n >= 3u * kRrWindow * n_warps ? kRrWindow : n >= 3u * 64u * n_warps ? 64u : 32u;
+  const uint32_t n_windows = (n + win - 1) / win;
+  const uint32_t mode = static_cast<uint32_t>(g.mode);
+  const bool use_from = g.from != nullptr && mode == 2;
+  const bool defer_rev = mode == 2 && g.reverse_mode == 0 && p.has_bwd != 0;
+
+  L8RevQueue<CM> queue;  // lines that matched and wait for their table-driven reverse pass
 
   for (uint32_t wi = warp_global; wi < n_windows; wi += n_warps) {
     const uint32_t w0 = wi * win;
@@ -172,11 +194,11 @@ __device__ __forceinline__ void l8_run_ragged_rounds(const Lines8Params& p, cons
       const bool want_rev = l8_stream_lines<CM, CharT>(p, cx, buf0, buf1, lane, own, line, use_from, defer_rev, &end, &from);
       if (defer_rev) {
         const uint32_t rv = __ballot_sync(kFull, want_rev);
-        if (rv) enqueue(rv, line, end, from);
+        if (rv) queue.push(p, cx, lane, rv, line, end, from);
       }
     }
   }
-  if (qn) reverse_batch(qn);
+  queue.flush(p, cx, lane);
 }
 
 }  // namespace ndl
